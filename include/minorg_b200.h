@@ -1,0 +1,180 @@
+/* minorg_b200 - C ABI of the B200-native gRNA enumeration + off-target screen.
+ *
+ * The reference (rlrq/MINORg, pure Python) has no FFI of its own: the seam is Python-level and the
+ * arithmetic is delegated to `regex` (PAM scan) and to a `blastn` subprocess (screen, masks).  Each entry
+ * point below names the reference call it stands in for (paths under /root/reference/minorg/).
+ * INTEGRATION.md shows the ctypes binding a MINORg maintainer would add at each of those call sites.
+ *
+ * Conventions: every function returns 0 on success or a negative mg_status; the message of the last
+ * failure on the calling thread is mg_last_error().  Pointers named d_* are DEVICE pointers, all others
+ * are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ * Handles are owned by the library (mg_*_free).  Not re-entrant per handle.  Do not fork() after the
+ * first call.  Coordinates are 0-based, end-exclusive, per contig, forward strand (Biopython HSP
+ * convention, filter_grna.py:52-56).
+ */
+#ifndef MINORG_B200_H
+#define MINORG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MG_OK = 0,
+    MG_ERR_CUDA = -1,      /* a CUDA runtime call or kernel failed */
+    MG_ERR_ARG = -2,       /* invalid argument */
+    MG_ERR_NOMEM = -3,     /* host or device allocation failed */
+    MG_ERR_OVERFLOW = -4,  /* caller-provided output capacity too small (needed size is reported) */
+    MG_ERR_UNSUPPORTED = -5
+} mg_status;
+
+#define MG_MAX_GRNA_LEN 32   /* gRNA length limit of the device kernels */
+#define MG_MAX_PAM_LEN 16    /* longest fixed-length PAM alternative */
+#define MG_MAX_PAM_ALTS 32   /* alternatives a quantified PAM side may expand to */
+#define MG_MAX_PATTERN_UNITS 32
+#define MG_MAX_PATTERN_OPS 96
+#define MG_MAX_GAPS 3
+
+const char* mg_last_error(void);
+int mg_version(void);
+int mg_device_count(void);
+/* Select the device for the calling thread and report its name / SM count (either may be NULL). */
+int mg_init(int device, char* name_out, int name_cap, int* sm_count_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Genome store: 2-bit packed bases + 1-bit "invalid" plane resident in HBM.
+ * Stands in for the subject side of the reference's BLAST call and for IndexedFasta slicing
+ * (index.py:150-211; MINORg.py:2134-2136, 2066-2083).  Contigs are laid out in one global coordinate
+ * space separated by >= 64 invalid bases, so no window spans two contigs and positions beyond a contig
+ * end read as "mismatch with everything".  Any byte other than ACGTacgt is invalid.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mg_genome mg_genome;
+
+/* seq: concatenated ASCII contig sequences (host); contig i = seq[offsets[i], offsets[i+1]).  */
+int mg_genome_from_ascii(const char* seq, const int64_t* offsets, int n_contigs, void* stream, mg_genome** out);
+/* Same, with the ASCII bytes already on the device (synthetic-genome benchmarks). */
+int mg_genome_from_device_ascii(const char* d_seq, const int64_t* offsets, int n_contigs, void* stream,
+                                mg_genome** out);
+int mg_genome_n_contigs(const mg_genome* g);
+int64_t mg_genome_contig_length(const mg_genome* g, int contig);
+int64_t mg_genome_total_bases(const mg_genome* g);    /* sum of contig lengths (no padding) */
+int64_t mg_genome_device_bytes(const mg_genome* g);   /* HBM footprint of the packed planes */
+/* Decode bases [start,end) of a contig back to ASCII ('N' for invalid); test/debug aid. */
+int mg_genome_decode(const mg_genome* g, int contig, int64_t start, int64_t end, char* out);
+void mg_genome_free(mg_genome* g);
+
+/* Masked (on-target) intervals of this genome: replaces MINORg.masked[filename] + _is_offtarget_pos
+ * (MINORg.py:1953-1964, 1994-2000).  A hit is on-target iff its span lies inside ONE interval. */
+int mg_genome_set_masks(mg_genome* g, const int32_t* contig, const int64_t* start, const int64_t* end, int n,
+                        void* stream);
+
+/* K3 - exact-occurrence mask finder: replaces mask_identical/blast_mask (filter_grna.py:67-119):
+ * every interval of the genome equal to a query sequence end-to-end, on either strand (ACGT only,
+ * case-insensitive).  seqs = concatenated ASCII, sequence i = seqs[offsets[i], offsets[i+1]).
+ * Outputs (host arrays of capacity cap): sequence index, contig, start, end, strand (+1/-1).
+ * *n_found receives the number found even when it exceeds cap (then MG_ERR_OVERFLOW). */
+int mg_mask_find(const mg_genome* g, const char* seqs, const int64_t* offsets, int n_seqs, int64_t cap,
+                 int32_t* out_seq, int32_t* out_contig, int64_t* out_start, int64_t* out_end, int8_t* out_strand,
+                 int64_t* n_found, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PAM program: a PAM side ('five' = pattern before the gRNA, 'three' = after) expanded by the host to a
+ * finite union of fixed-length alternatives; position k of an alternative allows the ASCII bytes whose
+ * bit is set in allow[alt][k][byte>>5] (enumeration; case already folded in by the host) and the bases
+ * whose bit is set in allow4[alt][k] (bit 0..3 = A,C,G,T; PAM proximity check on the 2-bit genome).
+ * Mirrors what PAM.regex()/five_prime()/three_prime() hand to `regex` (pam.py:103-125, 150-167).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_alts;                                   /* 0 = this side is empty */
+    int32_t len[MG_MAX_PAM_ALTS];
+    uint32_t allow[MG_MAX_PAM_ALTS][MG_MAX_PAM_LEN][8];
+    uint8_t allow4[MG_MAX_PAM_ALTS][MG_MAX_PAM_LEN];
+} mg_pam_side;
+
+typedef struct {
+    mg_pam_side five;
+    mg_pam_side three;
+    int32_t five_maxlen;    /* PAM.five_prime_maxlen(), including its documented over-count (pam.py:128-147) */
+    int32_t three_maxlen;
+} mg_pam;
+
+/* K2 - PAM-site enumeration: replaces the regex.finditer(overlapped=True) scan of both strands in
+ * find_multi_gRNA (generate_grna.py:38-41).  seq = one target record (ASCII, case preserved).  Outputs
+ * the ascending match starts on the '+' strand and on the '-' strand (positions in the reverse-complemented
+ * record, exactly like the reference's loop); capacities cap each; counts are reported even on overflow. */
+int mg_enumerate_sites(const char* seq, int64_t len, const mg_pam* pam, int grna_len, int64_t cap,
+                       int64_t* out_plus, int64_t* n_plus, int64_t* out_minus, int64_t* n_minus, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gRNA set resident in HBM: N sequences of one length L (ASCII, any case; non-ACGT = mismatch with
+ * everything).  Holds both orientations (query i = gRNA i, query N+i = its reverse complement) and the
+ * bit-sliced mismatch tables of the scan kernel.  Replaces the gRNA FASTA handed to blastn
+ * (MINORg.py:2134-2135).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mg_queries mg_queries;
+int mg_queries_create(const char* grna, int n, int len, void* stream, mg_queries** out);
+int mg_queries_count(const mg_queries* q);
+int mg_queries_length(const mg_queries* q);
+void mg_queries_free(mg_queries* q);
+
+/* Off-target criteria = the reference attributes that decide a hit (MINORg.py:686-707, 2018-2102).
+ * max_mismatch = max(1, ot_mismatch) - 1, max_gap = max(1, ot_gap) - 1 (MINORg.py:2033-2034).
+ * Pattern mode (n_units > 0) replaces OffTargetExpression (ot_regex.py:124-356): unit u is true iff
+ * count(chars in slice) [+ unaligned] <= n; `ops` is the expression in postfix order:
+ * op >= 0 pushes unit op; MG_OP_AND / MG_OP_OR combine the two topmost values. */
+#define MG_OP_AND (-1)
+#define MG_OP_OR (-2)
+#define MG_CH_MISMATCH 1
+#define MG_CH_INS 2
+#define MG_CH_DEL 4
+#define MG_SLICE_NONE INT32_MIN
+typedef struct {
+    int32_t n;          /* threshold */
+    int32_t chars;      /* MG_CH_* mask of characters counted */
+    int32_t start, end; /* Python slice bounds from ot_range (MG_SLICE_NONE = None) */
+    int32_t rvs;        /* 1: slice the tuple whose deletions join the PREVIOUS position (blast.py:102-117) */
+    int32_t add_unaligned_m, add_unaligned_g; /* unaligned_as_mismatch / unaligned_as_gap apply to this unit */
+} mg_pattern_unit;
+
+typedef struct {
+    int32_t max_mismatch;
+    int32_t max_gap;
+    int32_t pamless;          /* 1 = skip the PAM proximity check (reference default) */
+    int32_t n_units;          /* 0 = no pattern (MINORg._is_offtarget_aln_nopattern) */
+    int32_t n_ops;
+    mg_pattern_unit units[MG_MAX_PATTERN_UNITS];
+    int32_t ops[MG_MAX_PATTERN_OPS];
+    int32_t prefilter_edits;  /* host-derived bound: pattern true => full-length edit cost <= this; <0 = unbounded */
+} mg_criteria;
+
+/* K4/K5 - exhaustive off-target screen of every resident gRNA against every window of the genome, both
+ * strands: replaces MINORg._offtarget_hits (blastn -task blastn-short + is_offtarget_hit per HSP,
+ * MINORg.py:2123-2144).  d_counts: DEVICE array of 2*N uint32 that is ADDED to (query i / N+i = plus /
+ * minus orientation of gRNA i): the number of problematic, unmasked alignments anchored in this genome.
+ * gRNA i fails the background check iff d_counts[i] + d_counts[N+i] > 0.  No early exit: every cell is
+ * evaluated.  window range [win_begin, win_end) in global coordinates selects a shard (pass 0, -1 for all).
+ * pam may be NULL when crit->pamless. */
+int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
+              int64_t win_begin, int64_t win_end, uint32_t* d_counts, void* stream);
+
+/* Host-buffer convenience around the calls above (the end-to-end path timed by bench.py "e2e"):
+ * ASCII genome + ASCII gRNAs in host memory -> H2D, pack, screen, D2H.  counts_out: N uint32 (both
+ * orientations summed). */
+int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
+                   const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                   const char* grna, int n, int len, const mg_criteria* crit, const mg_pam* pam,
+                   uint32_t* counts_out, void* stream);
+
+/* Layout of the global coordinate space (for sharding by chunk with a halo): global start of a contig. */
+int64_t mg_genome_contig_global_start(const mg_genome* g, int contig);
+int64_t mg_genome_global_length(const mg_genome* g);
+
+/* Integer-pipe microbenchmarks used for the roofline denominators of the scan kernel (bench.py):
+ * which: 0 = LOP3 (ALU pipe) lane-ops, 1 = shared-memory 32-bit loads (LSU).  Returns Gops/s in *gops. */
+int mg_microbench(int which, double* gops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINORG_B200_H */

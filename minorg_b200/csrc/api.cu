@@ -1,0 +1,134 @@
+// C-ABI glue: screen dispatch, host-buffer convenience path, integer-pipe microbenchmarks.
+#include "common.cuh"
+
+using namespace mg;
+
+namespace mg {
+
+// ---------------------------------------------------------------- integer-pipe microbenchmarks
+// Denominators for the scan kernel's roofline (MEASURED_PEAKS.json only has HBM and bf16 numbers).
+__global__ void __launch_bounds__(1024, 1) ubench_lop3(uint32_t* out, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u, b = blockIdx.x * 40503u + 1u, c = a ^ 0x9E3779B9u, d = b + 77u;
+    uint32_t e = a + 1, f = b + 2, g = c + 3, h = d + 4;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // 8 independent LOP3 chains x 8 = 64 LOP3 per iteration
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b) : "r"(c), "r"(d));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(c) : "r"(d), "r"(e));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(d) : "r"(e), "r"(f));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(e) : "r"(f), "r"(g));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(f) : "r"(g), "r"(h));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(a));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(h) : "r"(a), "r"(b));
+        }
+    }
+    if ((a ^ b ^ c ^ d ^ e ^ f ^ g ^ h) == 0x12345u) out[0] = a;
+}
+
+__global__ void __launch_bounds__(1024, 1) ubench_lds(uint32_t* out, int iters) {
+    __shared__ uint32_t sm[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i * 2654435761u;
+    __syncthreads();
+    uint32_t acc = 0;
+    uint32_t idx = (threadIdx.x & 3u) + 4u * (threadIdx.x >> 5);    // 4 consecutive banks per warp, like the scan
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(sm + ((idx + 4u * u) & 4095u))));
+            acc ^= v;
+        }
+        idx += 128u;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
+}  // namespace mg
+
+extern "C" {
+
+int mg_microbench(int which, double* gops, void* stream) {
+    MG_CHECK_ARG(gops != nullptr && (which == 0 || which == 1));
+    cudaStream_t s = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    MG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t* d = nullptr;
+    MG_CUDA(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    MG_CUDA(cudaEventCreate(&e0));
+    MG_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        MG_CUDA(cudaEventRecord(e0, s));
+        if (which == 0) ubench_lop3<<<sms, 1024, 0, s>>>(d, iters);
+        else ubench_lds<<<sms, 1024, 0, s>>>(d, iters);
+        MG_CUDA(cudaEventRecord(e1, s));
+        MG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        MG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : 32.0);
+        const double r = ops / (ms * 1e-3) / 1e9;
+        if (rep > 0 && r > best) best = r;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *gops = best;
+    return MG_OK;
+}
+
+int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
+              int64_t win_begin, int64_t win_end, uint32_t* d_counts, void* stream) {
+    MG_CHECK_ARG(g && q && crit && d_counts);
+    MG_CHECK_ARG(crit->max_mismatch >= 0 && crit->max_gap >= 0 && crit->max_gap <= MG_MAX_GAPS);
+    MG_CHECK_ARG(crit->pamless || pam != nullptr);
+    MG_CHECK_ARG(crit->n_units >= 0 && crit->n_units <= MG_MAX_PATTERN_UNITS && crit->n_ops >= 0 && crit->n_ops <= MG_MAX_PATTERN_OPS);
+    const int L = q->len;
+    // every window start that can hold an alignment: from the first base of padding before contig 0
+    const int64_t last = g->glen - L;            // buffers carry spare words beyond glen
+    if (win_begin < 0) win_begin = 0;
+    if (win_end < 0 || win_end > last + 1) win_end = last + 1;
+    if (win_end <= win_begin || q->n == 0) return MG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool fast = crit->n_units == 0 && crit->max_gap == 0 && crit->pamless;
+    if (fast) {
+        if (crit->max_mismatch >= L) { set_error("mismatch budget %d >= gRNA length %d", crit->max_mismatch, L); return MG_ERR_ARG; }
+        return launch_screen_bitsliced(g, q, crit->max_mismatch, win_begin, win_end, d_counts, s);
+    }
+    return launch_screen_general(g, q, crit, pam, win_begin, win_end, d_counts, s);
+}
+
+int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
+                   const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                   const char* grna, int n, int len, const mg_criteria* crit, const mg_pam* pam,
+                   uint32_t* counts_out, void* stream) {
+    MG_CHECK_ARG(counts_out != nullptr || n == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    mg_genome* g = nullptr;
+    mg_queries* q = nullptr;
+    uint32_t* d_counts = nullptr;
+    int rc = mg_genome_from_ascii(seq, offsets, n_contigs, stream, &g);
+    if (rc == MG_OK) rc = mg_genome_set_masks(g, mask_contig, mask_start, mask_end, n_masks, stream);
+    if (rc == MG_OK) rc = mg_queries_create(grna, n, len, stream, &q);
+    if (rc == MG_OK && n > 0) {
+        if (cudaMalloc(&d_counts, sizeof(uint32_t) * 2 * (size_t)n) != cudaSuccess) { set_error("cudaMalloc(counts) failed"); rc = MG_ERR_NOMEM; }
+    }
+    if (rc == MG_OK && n > 0) {
+        cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * 2 * (size_t)n, s);
+        rc = mg_screen(g, q, crit, pam, 0, -1, d_counts, stream);
+    }
+    if (rc == MG_OK && n > 0) {
+        std::vector<uint32_t> tmp(2 * (size_t)n);
+        cudaError_t e = cudaMemcpyAsync(tmp.data(), d_counts, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("screen failed: %s", cudaGetErrorString(e)); rc = MG_ERR_CUDA; }
+        else for (int i = 0; i < n; ++i) counts_out[i] = tmp[i] + tmp[(size_t)n + i];
+    }
+    cudaFree(d_counts);
+    mg_queries_free(q);
+    mg_genome_free(g);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// Shared declarations of libminorg_b200 (sm_100a).  See include/minorg_b200.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/minorg_b200.h"
+
+namespace mg {
+
+void set_error(const char* fmt, ...);
+
+#define MG_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            mg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return MG_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define MG_CHECK_ARG(cond)                                                    \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            mg::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond); \
+            return MG_ERR_ARG;                                                \
+        }                                                                     \
+    } while (0)
+
+constexpr int kPad = 64;        // invalid bases between contigs (>= L + gaps + PAM flank)
+constexpr int kAlign = 32;      // contig global starts are multiples of this (one invalid-plane word)
+constexpr int kCodeInvalid = 4;
+
+// What the kernels see of a genome.
+struct GenomeView {
+    const uint32_t* bases;    // 2 bits/base, 16 bases per word, base i at bits [2(i%16), 2(i%16)+1]
+    const uint32_t* invalid;  // 1 bit/base, 32 bases per word
+    int64_t glen;             // global length in bases (multiple of 32; buffers hold 4 spare words)
+    const int64_t* cstart;    // [n_contigs] global start (sorted ascending)
+    const int64_t* cend;      // [n_contigs] global end
+    int n_contigs;
+    const int64_t* mstart;    // [n_masks] global mask starts, ascending
+    const int64_t* mend_pm;   // [n_masks] running maximum of global mask ends
+    int n_masks;
+};
+
+struct QueriesView {
+    const uint8_t* codes;     // [2N][L] base codes 0..3, 4 = invalid; query N+i = revcomp of gRNA i
+    const uint32_t* tab;      // [n_groups][4L+1] bit-sliced mismatch words (+ one all-ones word)
+    int n;                    // N
+    int len;                  // L
+    int n_groups;             // ceil(2N/32)
+};
+
+__device__ __forceinline__ uint32_t ld_bases(const uint32_t* p) { return __ldg(p); }
+
+// Bases [p, p+32) as 64 bits (lo = bases 0..15) and their invalid bits.
+__device__ __forceinline__ void load_window(const GenomeView& g, int64_t p, uint32_t& lo, uint32_t& hi, uint32_t& inv) {
+    const int64_t wi = p >> 4;
+    const unsigned sh = (unsigned)(p & 15) * 2u;
+    const uint32_t b0 = __ldg(g.bases + wi), b1 = __ldg(g.bases + wi + 1), b2 = __ldg(g.bases + wi + 2);
+    lo = __funnelshift_r(b0, b1, sh);
+    hi = __funnelshift_r(b1, b2, sh);
+    const int64_t ii = p >> 5;
+    inv = __funnelshift_r(__ldg(g.invalid + ii), __ldg(g.invalid + ii + 1), (unsigned)(p & 31));
+}
+
+__device__ __forceinline__ int base_at(const GenomeView& g, int64_t p) {   // 0..3 or 4
+    if (p < 0 || p >= g.glen) return kCodeInvalid;
+    if ((__ldg(g.invalid + (p >> 5)) >> (p & 31)) & 1u) return kCodeInvalid;
+    return (__ldg(g.bases + (p >> 4)) >> ((p & 15) * 2)) & 3u;
+}
+
+// Index of the contig whose [cstart - kPad/2, cend + kPad/2) neighbourhood holds p, or -1.
+__device__ __forceinline__ int contig_of(const GenomeView& g, int64_t p) {
+    int lo = 0, hi = g.n_contigs - 1, ans = -1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g.cstart[mid] - kPad / 2 <= p) { ans = mid; lo = mid + 1; } else hi = mid - 1;
+    }
+    return ans;
+}
+
+// True iff [a,b) (global) lies inside a single masked interval.
+__device__ __forceinline__ bool span_masked(const GenomeView& g, int64_t a, int64_t b) {
+    int lo = 0, hi = g.n_masks - 1, ans = -1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g.mstart[mid] <= a) { ans = mid; lo = mid + 1; } else hi = mid - 1;
+    }
+    return ans >= 0 && g.mend_pm[ans] >= b;
+}
+
+}  // namespace mg
+
+// Concrete handle types behind the opaque C names.
+struct mg_genome {
+    int device = 0;
+    int n_contigs = 0;
+    std::vector<int64_t> clen, cstart, cend;   // host copies
+    int64_t glen = 0;                           // global length (bases)
+    int64_t total = 0;
+    uint32_t* d_bases = nullptr;
+    uint32_t* d_invalid = nullptr;
+    int64_t* d_cstart = nullptr;
+    int64_t* d_cend = nullptr;
+    int64_t* d_mstart = nullptr;
+    int64_t* d_mend_pm = nullptr;
+    int n_masks = 0;
+    size_t bases_words = 0, invalid_words = 0;
+    mg::GenomeView view() const {
+        mg::GenomeView v;
+        v.bases = d_bases; v.invalid = d_invalid; v.glen = glen; v.cstart = d_cstart; v.cend = d_cend;
+        v.n_contigs = n_contigs; v.mstart = d_mstart; v.mend_pm = d_mend_pm; v.n_masks = n_masks;
+        return v;
+    }
+};
+
+struct mg_queries {
+    int n = 0, len = 0, n_groups = 0;
+    uint8_t* d_codes = nullptr;
+    uint32_t* d_tab = nullptr;
+    mg::QueriesView view() const {
+        mg::QueriesView v;
+        v.codes = d_codes; v.tab = d_tab; v.n = n; v.len = len; v.n_groups = n_groups;
+        return v;
+    }
+};
+
+namespace mg {
+// kernels / launchers implemented across the .cu files
+int launch_pack(const char* d_ascii, const std::vector<int64_t>& offsets, mg_genome* g, cudaStream_t s);
+int launch_build_queries(const char* d_ascii, mg_queries* q, cudaStream_t s);
+int launch_screen_bitsliced(const mg_genome* g, const mg_queries* q, int max_mismatch, int64_t wb, int64_t we,
+                            uint32_t* d_counts, cudaStream_t s);
+int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
+                          int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s);
+}  // namespace mg

@@ -1,0 +1,95 @@
+// gRNA set resident in HBM: base codes of both orientations + the bit-sliced mismatch tables of the
+// scan kernel.  Replaces the gRNA FASTA the reference hands to blastn (MINORg.py:2134-2135).
+#include "common.cuh"
+
+namespace mg {
+
+__device__ __forceinline__ int ascii_code(unsigned char c) {
+    const unsigned ch = c & 0xDFu;
+    const bool ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
+    unsigned code = (ch >> 1) & 3u;
+    code ^= (code >> 1);
+    return ok ? (int)code : kCodeInvalid;
+}
+
+// codes[q][j]: q < N forward gRNA, q >= N reverse complement of gRNA q-N.
+__global__ void query_codes_kernel(const char* __restrict__ ascii, int n, int len, uint8_t* __restrict__ codes) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * n * len) return;
+    const int q = idx / len, j = idx % len;
+    int c;
+    if (q < n) {
+        c = ascii_code((unsigned char)ascii[(size_t)q * len + j]);
+    } else {
+        c = ascii_code((unsigned char)ascii[(size_t)(q - n) * len + (len - 1 - j)]);
+        if (c != kCodeInvalid) c = 3 - c;
+    }
+    codes[idx] = (uint8_t)c;
+}
+
+// tab[g][4j+b] bit i = 1 iff query 32g+i does NOT have base b at position j (or is padding);
+// tab[g][4L] = all ones (looked up for an invalid genome base).
+__global__ void query_table_kernel(const uint8_t* __restrict__ codes, int nq, int len, int n_groups,
+                                   uint32_t* __restrict__ tab) {
+    const int stride = 4 * len + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_groups * stride) return;
+    const int g = idx / stride, slot = idx % stride;
+    uint32_t w = 0xFFFFFFFFu;
+    if (slot < 4 * len) {
+        const int j = slot >> 2, b = slot & 3;
+        w = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int q = g * 32 + i;
+            const bool mism = (q >= nq) || (codes[(size_t)q * len + j] != b);
+            w |= (mism ? 1u : 0u) << i;
+        }
+    }
+    tab[idx] = w;
+}
+
+int launch_build_queries(const char* d_ascii, mg_queries* q, cudaStream_t s) {
+    const int total = 2 * q->n * q->len;
+    if (total > 0) query_codes_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_ascii, q->n, q->len, q->d_codes);
+    const int words = q->n_groups * (4 * q->len + 1);
+    if (words > 0) query_table_kernel<<<(words + 255) / 256, 256, 0, s>>>(q->d_codes, 2 * q->n, q->len, q->n_groups, q->d_tab);
+    MG_CUDA(cudaGetLastError());
+    return MG_OK;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+int mg_queries_create(const char* grna, int n, int len, void* stream, mg_queries** out) {
+    MG_CHECK_ARG(out != nullptr && n >= 0 && len >= 1 && len <= MG_MAX_GRNA_LEN && (n == 0 || grna != nullptr));
+    MG_CHECK_ARG((int64_t)n * 2 * len < (int64_t)1 << 31);
+    cudaStream_t s = (cudaStream_t)stream;
+    mg_queries* q = new mg_queries();
+    q->n = n; q->len = len; q->n_groups = (2 * n + 31) / 32;
+    const size_t nbytes = (size_t)n * len;
+    char* d_ascii = nullptr;
+    MG_CUDA(cudaMalloc(&d_ascii, nbytes + 16));
+    MG_CUDA(cudaMalloc(&q->d_codes, 2 * nbytes + 16));
+    MG_CUDA(cudaMalloc(&q->d_tab, ((size_t)q->n_groups * (4 * len + 1) + 4) * 4));
+    if (nbytes) MG_CUDA(cudaMemcpyAsync(d_ascii, grna, nbytes, cudaMemcpyHostToDevice, s));
+    int rc = launch_build_queries(d_ascii, q, s);
+    cudaStreamSynchronize(s);
+    cudaFree(d_ascii);
+    if (rc) { mg_queries_free(q); return rc; }
+    *out = q;
+    return MG_OK;
+}
+
+int mg_queries_count(const mg_queries* q) { return q ? q->n : 0; }
+int mg_queries_length(const mg_queries* q) { return q ? q->len : 0; }
+
+void mg_queries_free(mg_queries* q) {
+    if (!q) return;
+    cudaFree(q->d_codes); cudaFree(q->d_tab);
+    delete q;
+}
+
+}  // extern "C"

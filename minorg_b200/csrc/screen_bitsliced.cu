@@ -1,0 +1,172 @@
+// K4: bit-sliced ungapped mismatch scan (the hot kernel).
+//
+// Replaces, for the reference's default criteria (no --ot-pattern, ot_gap <= 1, ot_pamless), the whole of
+// MINORg._offtarget_hits: `blastn -task blastn-short` + is_offtarget_hit per HSP (MINORg.py:2123-2144,
+// criterion MINORg.py:2018-2044, position check MINORg.py:1994-2000).
+//
+// Formulation.  Queries (gRNAs in both orientations) are grouped 32 to a 32-bit word, bit i = query i of
+// the group.  For gRNA position j and genome base b the table word T[g][4j+b] has bit i set iff query i
+// does NOT have base b at position j.  A thread owns ONE genome window p; the mismatch word of the group
+// against that window at position j is T[g][4j + base(p+j)] - one conflict-free shared-memory load (the
+// 32 lanes of a warp hit at most 4 consecutive banks + broadcast).  The L words are summed per bit with a
+// carry-save adder tree of LOP3 full adders (csa_gen.cuh) and compared with the mismatch budget, giving
+// 32 verdicts per ~(L loads + 1.9 L logic ops): ~2 lane-instructions per (gRNA, window, strand) cell,
+// all on the full-rate ALU/LSU pipes, against ~10 for a per-cell XOR/POPC.  Hits are rare (4e-7 per cell
+// at <=4 mismatches on random sequence), so the mask lookup and the per-gRNA counting live in a cold path.
+//
+// The kernel is bound by the LSU (L x 4 B per lane per 32 cells from shared memory at 128 B/clk/SM) and by
+// the ALU pipe (~39 LOP3 per 32 cells at L=20) at about the same level; HBM traffic is the packed genome
+// once per query chunk (0.375 B/base) and is three orders of magnitude below the HBM roofline.
+#include "common.cuh"
+#include "csa_gen.cuh"
+
+namespace mg {
+
+template <int NB>
+__device__ __forceinline__ uint32_t le_const_impl(const uint32_t (&b)[NB], int K) {
+    // bit i of the result = (count_i <= K); with K a compile-time constant this folds to ~NB/2 LOP3.
+    uint32_t lt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = NB - 1; k >= 0; --k) {
+        if ((K >> k) & 1) { lt |= eq & ~b[k]; eq &= b[k]; }
+        else              { eq &= ~b[k]; }
+    }
+    return lt | eq;
+}
+
+template <int NB>
+__device__ __forceinline__ uint32_t le_runtime(const uint32_t (&b)[NB], int K) {
+    uint32_t lt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = NB - 1; k >= 0; --k) {
+        const uint32_t kb = 0u - (uint32_t)((K >> k) & 1);      // warp-uniform all-ones / zero
+        lt |= eq & ~b[k] & kb;
+        eq &= ~(b[k] ^ kb);
+    }
+    return lt | eq;
+}
+
+// Cold path: some query of group `group` is within budget at window p.
+__device__ __noinline__ void report_hits(const GenomeView& gv, int n_queries, int L, uint32_t hit, int group,
+                                         int64_t p, uint32_t* __restrict__ counts) {
+    const int c = contig_of(gv, p);
+    if (c < 0) return;
+    const int64_t a = max(p, gv.cstart[c]), b = min(p + L, gv.cend[c]);   // on-contig span of the window
+    if (a >= b) return;
+    if (gv.n_masks && span_masked(gv, a, b)) return;                      // on-target (MINORg.py:1994-2000)
+    while (hit) {
+        const int i = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const int q = group * 32 + i;
+        if (q < n_queries) atomicAdd(counts + q, 1u);
+    }
+}
+
+template <int L, int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chunk, int64_t wb, int64_t we,
+                        uint32_t* __restrict__ counts) {
+    constexpr int S = 4 * L + 1;                     // table words per group
+    constexpr int NB = mgcsa::CountBits<L>::value;
+    extern __shared__ uint32_t tab[];
+
+    // contiguous, warp-aligned window range of this CTA
+    const int64_t nwin = we - wb;
+    int64_t per = (nwin + gridDim.x - 1) / gridDim.x;
+    per = (per + 31) / 32 * 32;
+    const int64_t w0 = wb + (int64_t)blockIdx.x * per;
+    const int64_t w1 = min(we, w0 + per);
+
+    for (int cg = 0; cg < qv.n_groups; cg += groups_per_chunk) {
+        const int ng = min(groups_per_chunk, qv.n_groups - cg);
+        __syncthreads();
+        {   // stage this chunk of the query tables: coalesced 32-bit copies (the table is L2-resident)
+            const uint32_t* src = qv.tab + (size_t)cg * S;
+            for (int i = threadIdx.x; i < ng * S; i += THREADS) tab[i] = __ldg(src + i);
+        }
+        __syncthreads();
+
+        for (int64_t pbase = w0; pbase < w1; pbase += THREADS) {
+            const int64_t p = pbase + threadIdx.x;
+            const bool active = p < w1;
+            uint32_t off[L];
+            {
+                uint32_t lo = 0, hi = 0, inv = 0xFFFFFFFFu;
+                if (active) load_window(gv, p, lo, hi, inv);
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    const uint32_t code = (j < 16) ? ((lo >> (2 * j)) & 3u) : ((hi >> (2 * (j - 16))) & 3u);
+                    off[j] = (((inv >> j) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * j) + code) * 4u;   // byte offset
+                }
+            }
+            const char* t = reinterpret_cast<const char*>(tab);
+#pragma unroll 1
+            for (int g = 0; g < ng; ++g, t += S * 4) {
+                uint32_t x[L];
+#pragma unroll
+                for (int j = 0; j < L; ++j) x[j] = *reinterpret_cast<const uint32_t*>(t + off[j]);
+                uint32_t bits[NB];
+                mgcsa::csa_count<L>(x, bits);
+                const uint32_t hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
+                if (hit) report_hits(gv, 2 * qv.n, L, hit, cg + g, p, counts);
+            }
+        }
+    }
+}
+
+template <int L, int K>
+static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t wb, int64_t we, uint32_t* d_counts,
+                      cudaStream_t s) {
+    constexpr int THREADS = 1024;
+    constexpr int S = 4 * L + 1;
+    int dev = 0, sms = 0, smem_max = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    MG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MG_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int max_groups = (smem_max - 1024) / (S * 4);
+    const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
+    const size_t smem = (size_t)gpc * S * 4;
+    auto kern = screen_bitsliced_kernel<L, K, THREADS>;
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t nwin = we - wb;
+    int64_t grid = (nwin + THREADS - 1) / THREADS;
+    if (grid > sms) grid = sms;             // persistent: one CTA per SM, each owns a contiguous genome slice
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts);
+    MG_CUDA(cudaGetLastError());
+    return MG_OK;
+}
+
+template <int L>
+static int dispatch_k(const mg_genome* g, const mg_queries* q, int k, int64_t wb, int64_t we, uint32_t* c, cudaStream_t s) {
+    switch (k) {
+        case 0: return launch_one<L, 0>(g, q, k, wb, we, c, s);
+        case 1: return launch_one<L, 1>(g, q, k, wb, we, c, s);
+        case 2: return launch_one<L, 2>(g, q, k, wb, we, c, s);
+        case 3: return launch_one<L, 3>(g, q, k, wb, we, c, s);
+        case 4: return launch_one<L, 4>(g, q, k, wb, we, c, s);
+        case 5: return launch_one<L, 5>(g, q, k, wb, we, c, s);
+        default: return launch_one<L, -1>(g, q, k, wb, we, c, s);
+    }
+}
+
+int launch_screen_bitsliced(const mg_genome* g, const mg_queries* q, int max_mismatch, int64_t wb, int64_t we,
+                            uint32_t* d_counts, cudaStream_t s) {
+    if (q->n == 0 || we <= wb) return MG_OK;
+    const int k = max_mismatch;
+    switch (q->len) {
+#define MG_CASE_FULL(LL) case LL: return dispatch_k<LL>(g, q, k, wb, we, d_counts, s);
+#define MG_CASE_RT(LL) case LL: return launch_one<LL, -1>(g, q, k, wb, we, d_counts, s);
+        MG_CASE_FULL(20) MG_CASE_FULL(23)
+        MG_CASE_RT(1) MG_CASE_RT(2) MG_CASE_RT(3) MG_CASE_RT(4) MG_CASE_RT(5) MG_CASE_RT(6) MG_CASE_RT(7) MG_CASE_RT(8)
+        MG_CASE_RT(9) MG_CASE_RT(10) MG_CASE_RT(11) MG_CASE_RT(12) MG_CASE_RT(13) MG_CASE_RT(14) MG_CASE_RT(15)
+        MG_CASE_RT(16) MG_CASE_RT(17) MG_CASE_RT(18) MG_CASE_RT(19) MG_CASE_RT(21) MG_CASE_RT(22) MG_CASE_RT(24)
+        MG_CASE_RT(25) MG_CASE_RT(26) MG_CASE_RT(27) MG_CASE_RT(28) MG_CASE_RT(29) MG_CASE_RT(30) MG_CASE_RT(31)
+        MG_CASE_RT(32)
+#undef MG_CASE_FULL
+#undef MG_CASE_RT
+        default: set_error("gRNA length %d unsupported (1..32)", q->len); return MG_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace mg

@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""Generate golden vectors by EXECUTING the reference's own Python code in this container.
+
+Run:  python tests/golden/make_golden.py      (needs /root/reference; writes tests/golden/*.json)
+
+What is executed verbatim from /root/reference (with the third-party stand-ins of refshim.py):
+  * minorg.pam.PAM                               -> pam.json
+  * minorg.ot_regex.ot_range                     -> ot_range.json
+  * minorg.blast.BlastHSP + minorg.ot_regex.OffTargetExpression  -> ot_pattern.json
+  * minorg.MINORg.MINORg._is_offtarget_aln_nopattern / _has_pam / _is_offtarget_pos (unbound, on a
+    stand-in `self`), minorg.filter_grna.Masked   -> criteria.json and screen_*.json
+  * minorg.generate_grna.find_multi_gRNA + gRNAHits.write_fasta/write_mapping  -> enumerate.json
+
+screen_*.json: tiny genomes; EVERY local alignment of the E1 universe (contiguous
+query sub-range, first/last column a base pair, <= Gcap gap characters strictly inside) is enumerated
+here and judged by the reference's three predicates (pos AND aln AND pam, MINORg.py:2105-2121); a gRNA
+fails iff any alignment is judged problematic.  Only the enumeration of the universe is ours; every
+verdict is the reference's.
+
+The test-suite never imports this file; it only reads the JSON it wrote.
+"""
+import io
+import json
+import os
+import random
+import sys
+import contextlib
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+warnings.simplefilter("ignore")
+import refshim  # noqa: E402
+
+refshim.install()
+
+with contextlib.redirect_stdout(io.StringIO()):
+    import minorg.MINORg as refM  # noqa: E402
+    from minorg.pam import PAM as RefPAM  # noqa: E402
+    from minorg.ot_regex import ot_range as ref_ot_range, OffTargetExpression as RefOTE  # noqa: E402
+    from minorg.blast import BlastHSP as RefBlastHSP  # noqa: E402
+    from minorg.filter_grna import Masked as RefMasked  # noqa: E402
+    from minorg.generate_grna import find_multi_gRNA as ref_find_multi_gRNA  # noqa: E402
+    from minorg import MINORgError  # noqa: E402
+
+
+def quiet(f, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+class Obj:
+    def __init__(self, **k):
+        self.__dict__.update(k)
+
+
+def dump(name, obj):
+    path = os.path.join(HERE, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, indent=None, separators=(",", ":"), sort_keys=True)
+        f.write("\n")
+    print("wrote", name, os.path.getsize(path), "bytes")
+
+
+# ----------------------------------------------------------------------------- PAM
+def gen_pam():
+    pams = ["GG", "NGG", ".NGG", "ngg", ".GG", "TTN", "TTTV.", "DTTN.", ".NGRRT", ".NGRRN", ".NNNNRYAC",
+            "T{3}V.", "R{1,2}T", ".", "NG", ".NG", "TTTN.", "ATV.", "YG", "NNGRRT", ".NNAGAAW", "TTV.",
+            "N", "G", "tttv.", ".NGA", "BGG.", "NGGNG", "KTTV.", "A.", ".A", "NAA.", "[AG]GG", ".N[AG]G", "TT[ACG]."]
+    rows = []
+    for pam in pams:
+        for L in (20, 23, 1):
+            try:
+                p = RefPAM(pam=pam, gRNA_length=L)
+                row = dict(pam=pam, L=L, parsed=p.pam, regex=quiet(p.regex).pattern,
+                           five=p.five_prime(), three=p.three_prime(),
+                           five_max=p.five_prime_maxlen(), three_max=p.three_prime_maxlen())
+            except Exception as e:  # e.g. more than one '.' -> ValueError on split
+                row = dict(pam=pam, L=L, error=type(e).__name__)
+            rows.append(row)
+    # copy-constructor quirk (pam.py:37-42)
+    src = RefPAM(pam="TTTV.", gRNA_length=23)
+    cc = [dict(src_L=23, arg_L=a, got_L=RefPAM(pam=src, gRNA_length=a).gRNA_length) for a in (20, 25, None)]
+    dump("pam.json", dict(rows=rows, copy_ctor=cc))
+
+
+# ----------------------------------------------------------------------------- ot_range
+def gen_ot_range():
+    cases = ["5", "-5", "5-", "-5-", "2-4", "-2--4", "1", "-1", "1-", "-1-", "20", "-20", "10-", "-10-",
+             "-11-", "11-", "3-3", "-3--3", "4-2", "-4--2", "0", "-0", "0-3", "2-0", "-2-4", "2--4", "", "a",
+             "1-20", "-1--20", "6-", "-6-", "7-15", "-7--15", "--5", "5--", "12", "-12"]
+    rows = []
+    for c in cases:
+        try:
+            r = quiet(ref_ot_range, c)
+            rows.append(dict(range=c, out=list(r)))
+        except MINORgError:
+            rows.append(dict(range=c, error=True))
+    dump("ot_range.json", dict(rows=rows))
+
+
+# ----------------------------------------------------------------------------- alignments / patterns
+BASES = "ACGT"
+
+
+def cols_to_btop(cols):
+    """cols: list of (kind, qbase, sbase) with kind in '.', 'm', 'i', 'd' -> BLAST BTOP string."""
+    out, run = [], 0
+    for kind, qb, sb in cols:
+        if kind == ".":
+            run += 1
+            continue
+        if run:
+            out.append(str(run))
+            run = 0
+        if kind == "m":
+            out.append(qb + sb)
+        elif kind == "i":      # base only in the gRNA (query): 'X-'
+            out.append(qb + "-")
+        else:                  # 'd': base only in the subject: '-Y'
+            out.append("-" + sb)
+    if run:
+        out.append(str(run))
+    return "".join(out)
+
+
+def random_alignment(rng, L, max_gap):
+    """Random local alignment of a length-L query: returns (btop, qstart, qend, kinds string)."""
+    qs = rng.choice([0, 0, 0, 1, 2, rng.randrange(0, max(1, L // 2))])
+    qe = L - rng.choice([0, 0, 0, 1, 2, rng.randrange(0, max(1, L // 2 - 1))])
+    if qe - qs < 2:
+        qs, qe = 0, L
+    n_q = qe - qs
+    kinds = []
+    gaps = 0
+    j = 0
+    while j < n_q:
+        first, last = (j == 0), (j == n_q - 1)
+        r = rng.random()
+        if not first and gaps < max_gap and r < 0.08:
+            kinds.append("d")          # subject-only column, consumes no query base
+            gaps += 1
+            continue
+        if not first and not last and gaps < max_gap and r < 0.16:
+            kinds.append("i")
+            gaps += 1
+            j += 1
+            continue
+        kinds.append("m" if r > 0.8 else ".")
+        j += 1
+    # a 'd' may not be the final column: strip trailing d's
+    while kinds and kinds[-1] == "d":
+        kinds.pop()
+    cols = []
+    for k in kinds:
+        qb = rng.choice(BASES)
+        sb = qb if k == "." else rng.choice([b for b in BASES if b != qb])
+        cols.append((k, qb, sb))
+    return cols_to_btop(cols), qs, qe, "".join(kinds)
+
+
+def gen_ot_pattern():
+    rng = random.Random(20261019)
+    patterns = ["0mg-10,1mg-11-", "1m-10,1mg-11-", "0mg5", "0m5", "1g20", "0g20", "0d-10", "0d10", "0d11-",
+                "0i-5", "0i-4", "(0mg5,1mg6-)|(0mg6,1m7-)", "0mg5,1mg6-|0mg6,1m7-", "0m-10|0m10",
+                "0g4|(2m4,0g5)", "0g4|(2m4,1g5)", "1m3,2g3", "2mg1-", "3m-1-", "1mi10,0d5-", "0md-8--3",
+                "1m2-4|0g-2--4", "((0m5))", "(1m10|0g10),2mg11-", "0m1", "0m-1", "4m1-,1g1-", "2m6-12,0g6-12",
+                "1g-15-", "0m-5-", "0mg-20", "5mg20", "1d3-,1i-18"]
+    alns = []
+    for L in (20, 20, 20, 23, 12):
+        for _ in range(14):
+            btop, qs, qe, kinds = random_alignment(rng, L, rng.choice([0, 1, 1, 2, 3]))
+            alns.append(dict(btop=btop, qstart=qs, qend=qe, qlen=L, kinds=kinds))
+    # the reference's own commented example (ot_regex.py:37-40) and SURVEY Appendix D alignments
+    alns.append(dict(btop="1AG-T12-TAG1", qstart=1, qend=21, qlen=20, kinds=None))
+    for btop, qs, qe in [("2AG14AG2", 0, 20), ("20", 0, 20), ("18", 2, 20), ("5-A15", 0, 20), ("15A-4", 0, 20),
+                         ("10AG9", 0, 20), ("10-A10", 0, 20), ("5-A-C15", 0, 20), ("3-A4-C4-G9", 0, 20)]:
+        alns.append(dict(btop=btop, qstart=qs, qend=qe, qlen=20, kinds=None))
+    rows = []
+    for a in alns:
+        hsp = Obj(btop=a["btop"], query_start=a["qstart"], query_end=a["qend"])
+        q = Obj(seq_len=a["qlen"])
+        b = RefBlastHSP(hsp, q, None)
+        a["sbtop"] = b.sbtop
+        a["tbtop"] = list(b.tbtop)
+        a["tbtop_rvs"] = list(b.tbtop_rvs)
+        res = {}
+        for pat in patterns:
+            for uam, uag in ((True, False), (False, False), (True, True), (False, True)):
+                key = "%s|%d%d" % (pat, uam, uag)
+                try:
+                    res[key] = bool(quiet(quiet(RefOTE, pat, unaligned_as_mismatch=uam, unaligned_as_gap=uag), b))
+                except Exception as e:
+                    res[key] = "error:" + type(e).__name__
+        a["results"] = res
+        rows.append(a)
+    bad = {}
+    for pat in ["1gi5", "1gd5", "m5", "1m", "1x5", "1m0", "", "1m5,", "(1m5", "1m5)"]:
+        try:
+            f = quiet(RefOTE, pat)
+            hsp = Obj(btop="20", query_start=0, query_end=20)
+            bad[pat] = bool(quiet(f, RefBlastHSP(hsp, Obj(seq_len=20), None)))
+        except Exception as e:
+            bad[pat] = "error:" + type(e).__name__
+    dump("ot_pattern.json", dict(patterns=patterns, rows=rows, odd_patterns=bad))
+
+
+# ----------------------------------------------------------------------------- criteria (per-HSP)
+class ClampSeq(refshim.Seq):
+    """Subject sequence whose slices clamp negative starts at the contig start (pyfaidx would wrap;
+    SURVEY Appendix B: the oracle clamps to the contig instead)."""
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            a = 0 if k.start is None else max(0, k.start)
+            b = len(self._d) if k.stop is None else max(0, k.stop)
+            return ClampSeq(self._d[a:b])
+        return self._d[k]
+
+    def reverse_complement(self):
+        return ClampSeq(str(refshim.Seq.reverse_complement(self)))
+
+
+def ref_self(ot_mismatch, ot_gap, pattern, uam, uag, pamless, pam, L, masks, fname="subject.fasta"):
+    s = Obj(ot_mismatch=ot_mismatch, ot_gap=ot_gap, ot_pamless=pamless, pam=RefPAM(pam=pam, gRNA_length=L))
+    if pattern is None:
+        s._ot_function = lambda hsp, qr: refM.MINORg._is_offtarget_aln_nopattern(s, hsp, qr)
+    else:
+        s.ot_pattern = quiet(RefOTE, pattern, unaligned_as_mismatch=uam, unaligned_as_gap=uag)
+        s._ot_function = lambda hsp, qr: refM.MINORg._is_offtarget_aln_pattern(s, hsp, qr)
+    s.masked = {fname: tuple(RefMasked(Obj(query_id=m[0], hit_id=m[1], hit_start=m[2], hit_end=m[3])) for m in masks)}
+    return s
+
+
+def gen_criteria():
+    rng = random.Random(7)
+    rows = []
+    for _ in range(400):
+        L = rng.choice([20, 20, 23])
+        om, og = rng.choice([0, 1, 2, 3, 5]), rng.choice([0, 1, 2, 3])
+        qs = rng.choice([0, 0, 1, 2, 3])
+        qe = L - rng.choice([0, 0, 1, 2, 3])
+        hsp = Obj(query_start=qs, query_end=qe, mismatch_num=rng.randrange(0, 6), gap_num=rng.randrange(0, 3))
+        s = Obj(ot_mismatch=om, ot_gap=og)
+        out = refM.MINORg._is_offtarget_aln_nopattern(s, hsp, Obj(seq_len=L))
+        rows.append(dict(L=L, ot_mismatch=om, ot_gap=og, qstart=qs, qend=qe, mm=hsp.mismatch_num,
+                         gaps=hsp.gap_num, problematic=bool(out)))
+    within = []
+    for _ in range(200):
+        ms, me = sorted(rng.sample(range(0, 60), 2))
+        hs = rng.randrange(0, 60)
+        he = hs + rng.randrange(1, 25)
+        m = RefMasked(Obj(query_id="t", hit_id="c", hit_start=ms, hit_end=me))
+        within.append(dict(mask=[ms, me], hit=[hs, he], within=bool(m.within((hs, he)))))
+    dump("criteria.json", dict(nopattern=rows, within=within))
+
+
+# ----------------------------------------------------------------------------- exhaustive screens
+COMP = str.maketrans("ACGTNacgtn", "TGCANtgcan")
+
+
+def rc(s):
+    return s.translate(COMP)[::-1]
+
+
+def enum_alignments(q, T, gcap):
+    """Yield every alignment of the E1 universe of query q against text T (one strand):
+    (qs, qe, s, t, cols) with cols a list of (kind, qbase, sbase)."""
+    L, n = len(q), len(T)
+    for qs in range(L):
+        for s in range(n):
+            # iterative DFS; state = (j, t, gaps, cols)
+            stack = [(qs, s, 0, [])]
+            while stack:
+                j, t, g, cols = stack.pop()
+                # pair column
+                if j < L and t < n:
+                    a, b = q[j].upper(), T[t].upper()
+                    same = (a == b) and (a in BASES)
+                    c2 = cols + [("." if same else "m", q[j], T[t])]
+                    yield (qs, j + 1, s, t + 1, c2)
+                    stack.append((j + 1, t + 1, g, c2))
+                if cols and g < gcap:
+                    if j < L:
+                        stack.append((j + 1, t, g + 1, cols + [("i", q[j], "-")]))
+                    if t < n:
+                        stack.append((j, t + 1, g + 1, cols + [("d", "-", T[t])]))
+
+
+def screen_with_reference(grnas, contigs, masks, crit):
+    """-> (fail flags, per-gRNA count of problematic alignments)."""
+    L = len(grnas[0])
+    gcap = max(1, crit["ot_gap"]) - 1
+    fname = "subject.fasta"
+    s = ref_self(crit["ot_mismatch"], crit["ot_gap"], crit.get("pattern"), crit.get("uam", True),
+                 crit.get("uag", False), crit["pamless"], crit["pam"], L, masks, fname)
+    ifasta = Obj(filename=fname)
+    seqs = {cid: ClampSeq(seq) for cid, seq in contigs}
+    ifasta.__class__ = type("IF", (Obj,), {"__getitem__": lambda self, k: seqs[k]})
+    fails, counts = [], []
+    for gi, q in enumerate(grnas):
+        qr = Obj(seq_len=L)
+        nprob = 0
+        for cid, seq in contigs:
+            n = len(seq)
+            for strand, T in ((1, seq), (-1, rc(seq))):
+                for qs, qe, a, b, cols in enum_alignments(q, T, gcap):
+                    hs, he = (a, b) if strand == 1 else (n - b, n - a)
+                    hsp = Obj(query_id="g%d" % gi, hit_id=cid, hit_start=hs, hit_end=he, hit_strand=strand,
+                              query_start=qs, query_end=qe, btop=cols_to_btop(cols),
+                              mismatch_num=sum(1 for c in cols if c[0] == "m"),
+                              gap_num=sum(1 for c in cols if c[0] in "id"))
+                    if not refM.MINORg._is_offtarget_pos(s, hsp, ifasta):
+                        continue
+                    if not quiet(s._ot_function, hsp, qr):
+                        continue
+                    if not (s.ot_pamless or refM.MINORg._has_pam(s, hsp, qr, ifasta)):
+                        continue
+                    nprob += 1
+        fails.append(nprob > 0)
+        counts.append(nprob)
+    return fails, counts
+
+
+def mutate(rng, s, nmm):
+    s = list(s)
+    for p in rng.sample(range(len(s)), nmm):
+        s[p] = rng.choice([b for b in BASES if b != s[p]])
+    return "".join(s)
+
+
+def make_case(rng, name, L, n_contigs, clen, crit, n_grna, with_n=False, with_masks=True):
+    contigs = []
+    for c in range(n_contigs):
+        n = rng.randrange(max(4, clen // 2), clen + 1) if c else clen
+        contigs.append(["ctg%d" % c, "".join(rng.choice(BASES) for _ in range(n))])
+    if n_contigs > 2:
+        contigs[-1][1] = contigs[-1][1][: max(3, L // 2)]      # a contig shorter than the gRNA
+    grnas = []
+    M = max(1, crit["ot_mismatch"]) - 1
+    gcap = max(1, crit["ot_gap"]) - 1
+    for i in range(n_grna):
+        cid = rng.randrange(len(contigs))
+        seq = contigs[cid][1]
+        kind = i % 6
+        if len(seq) < L + 2 or kind == 5:
+            grnas.append("".join(rng.choice(BASES) for _ in range(L)))
+            continue
+        p = rng.randrange(0, len(seq) - L - 1)
+        g = seq[p:p + L]
+        if kind == 1:
+            g = mutate(rng, g, M)
+        elif kind == 2:
+            g = mutate(rng, g, M + 1)
+        elif kind == 3 and gcap:
+            k = rng.randrange(2, L - 2)
+            g = (g[:k] + g[k + 1:] + rng.choice(BASES)) if rng.random() < .5 else (g[:k] + rng.choice(BASES) + g[k:])[:L]
+        elif kind == 4:           # hangs off a contig end
+            g = (seq[:L - 2] if rng.random() < .5 else seq[-(L - 2):])
+            g = ("".join(rng.choice(BASES) for _ in range(L - len(g))) + g) if rng.random() < .5 else \
+                (g + "".join(rng.choice(BASES) for _ in range(L - len(g))))
+        if rng.random() < 0.5:
+            g = rc(g)
+        grnas.append(g)
+    if with_n:
+        cid, seq = contigs[0]
+        p = rng.randrange(5, len(seq) - 8)
+        contigs[0][1] = seq[:p] + "NNN" + seq[p + 3:]
+        grnas[0] = grnas[0][:3] + "N" + grnas[0][4:]
+    masks = []
+    if with_masks:
+        for i in range(rng.randrange(1, 4)):
+            cid, seq = rng.choice(contigs)
+            if len(seq) < 12:
+                continue
+            a = rng.randrange(0, len(seq) - 8)
+            b = min(len(seq), a + rng.randrange(L - 4, L + 14))
+            masks.append(["tgt%d" % i, cid, a, b])
+    fails, counts = screen_with_reference(grnas, [tuple(c) for c in contigs], masks, crit)
+    print("  case", name, "fails", sum(fails), "/", len(fails))
+    return dict(name=name, L=L, contigs=contigs, grnas=grnas, masks=masks, criteria=crit, fail=fails,
+                n_problematic_alignments=counts)
+
+
+def gen_screens():
+    rng = random.Random(424242)
+    cases = []
+    base = dict(pattern=None, uam=True, uag=False, pamless=True, pam=".NGG")
+    # ungapped, PAM-less, no pattern (reduction (2) of SURVEY 8c): the fast path
+    for i, (om, L) in enumerate([(1, 20), (2, 20), (3, 20), (5, 20), (0, 20), (2, 23), (3, 12)]):
+        cases.append(make_case(rng, "hamming_%d" % i, L, 3, 120, dict(base, ot_mismatch=om, ot_gap=0), 12,
+                               with_n=(i % 2 == 0)))
+    # ungapped with PAM proximity check
+    for i, (om, pam, L) in enumerate([(2, ".NGG", 20), (3, "TTTV.", 23), (2, ".NGRRT", 20), (1, ".", 20), (3, "TTN", 12)]):
+        cases.append(make_case(rng, "pam_%d" % i, L, 2, 90, dict(base, ot_mismatch=om, ot_gap=0, pamless=False, pam=pam), 10))
+    # ungapped with pattern
+    for i, (pat, uam, uag) in enumerate([("0mg-10,1mg-11-", True, False), ("1m-8,2m9-", True, False),
+                                         ("0m5|1m-6", True, False), ("1m10,1m11-", False, False),
+                                         ("(0mg5,1mg6-)|(0mg6,1m7-)", True, True), ("2m1-", True, False)]):
+        cases.append(make_case(rng, "pattern_%d" % i, 20, 2, 80, dict(base, ot_mismatch=1, ot_gap=0, pattern=pat, uam=uam, uag=uag), 10))
+    # gapped (Gcap=1), shorter gRNA so the exhaustive enumeration stays cheap
+    for i, (om, og, pamless, pam) in enumerate([(1, 2, True, ".NGG"), (2, 2, True, ".NGG"), (3, 2, True, ".NGG"),
+                                                (2, 2, False, ".NGG"), (2, 2, False, "TTV.")]):
+        cases.append(make_case(rng, "gapped_%d" % i, 12, 2, 44, dict(base, ot_mismatch=om, ot_gap=og, pamless=pamless, pam=pam), 8))
+    for i, (pat, uam, uag) in enumerate([("0mg-6,1mg-7-", True, False), ("1mg1-", True, False), ("1m1-,1g1-", True, False),
+                                         ("0m6,1g-6", True, True), ("1mi-8,0d1-", True, False)]):
+        cases.append(make_case(rng, "gapped_pattern_%d" % i, 12, 2, 40, dict(base, ot_mismatch=1, ot_gap=2, pattern=pat, uam=uam, uag=uag), 8))
+    # two gaps: exercises the 'dd' grouping quirk of blast.py:114-116
+    for i, (pat, om) in enumerate([(None, 2), ("1m1-,2g1-", 1), ("0d5,2mg6-", 1)]):
+        cases.append(make_case(rng, "gap2_%d" % i, 10, 1, 30, dict(base, ot_mismatch=om, ot_gap=3, pattern=pat), 6, with_masks=(i == 0)))
+    dump("screen_cases.json", dict(cases=cases))
+
+
+# ----------------------------------------------------------------------------- enumeration
+SYNTH_FASTA = """>recA some description
+ACGTTGGCCAGGTTTACCGGAGGNGGCCTTTAACCGGTTAGGCCTTAGGGATCCAATTGGCCGG
+ccggaattccggAGGtttaaaccgGGTTTACG
+>recB
+TTTAGGCCNNNNNGGACCTTTGCGGCCAAGGTTRYGGACGTACGTAGGCATGCATGG
+
+>short
+ACGGG
+>recA
+GGCCAGGTTTACCGGAGGACGTTGGCCAGGTTTACCGGAGGTTTCGGCCAAAGG
+>iupac
+ACGTRYKMSWBDHVNACGGTTTACGATCGATCGGAGGCCTTTGNGGATTTCCGGAAGG
+"""
+
+
+def hits_dump(h):
+    out = []
+    for seq in h.seqs:
+        hs = sorted(h.get_hits(seq), key=lambda x: x.hit_id)
+        out.append([seq, [[x.target_id, x.range[0], x.range[1], x.strand, x.hit_id, x.target_len] for x in hs]])
+    return out
+
+
+def gen_enumerate():
+    import tempfile
+    synth = os.path.join(HERE, "synth_targets.fasta")
+    with open(synth, "w") as f:
+        f.write(SYNTH_FASTA)
+    rows = []
+    srcs = [("sample_CDS.fasta", "/root/reference/examples/sample_CDS.fasta"), ("synth_targets.fasta", synth)]
+    for label, path in srcs:
+        for pam, L in [(".NGG", 20), ("TTTV.", 20), ("ATV.", 20), ("TTTV.", 23), (".", 20), ("NG", 18), (".NGRRT", 21),
+                       ("T{3}V.", 20), ("R{1,2}T", 20), ("NGG", 70)]:
+            h = quiet(ref_find_multi_gRNA, path, pam=pam, gRNA_len=L)
+            row = dict(fasta=label, pam=pam, L=L, n_seqs=len(h), n_hits=sum(len(h.get_hits(s)) for s in h.seqs))
+            if label.startswith("synth") or (pam, L) in ((".NGG", 20), ("TTTV.", 23)):
+                row["hits"] = hits_dump(h)
+                with tempfile.TemporaryDirectory() as td:
+                    fa, mp = os.path.join(td, "g.fasta"), os.path.join(td, "g.map")
+                    if len(h):
+                        quiet(h.write_fasta, fa, write_all=True)
+                        quiet(h.write_mapping, mp, write_all=True, write_checks=True)
+                        row["fasta_text"] = open(fa).read()
+                        row["map_text"] = open(mp).read()
+            rows.append(row)
+    dump("enumerate.json", dict(rows=rows))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["pam", "ot_range", "ot_pattern", "criteria", "enumerate", "screens"]
+    if "pam" in which:
+        gen_pam()
+    if "ot_range" in which:
+        gen_ot_range()
+    if "ot_pattern" in which:
+        gen_ot_pattern()
+    if "criteria" in which:
+        gen_criteria()
+    if "enumerate" in which:
+        gen_enumerate()
+    if "screens" in which:
+        gen_screens()
