@@ -1,0 +1,40 @@
+"""gRNA candidate enumeration - drop-in for the reference's `find_multi_gRNA`
+(generate_grna.py:23-57): same signature, same gRNAHits content and order; the PAM scan of both strands of
+every target record runs on the GPU (K2, mg_enumerate_sites) instead of `regex.finditer`."""
+import numpy as np
+
+from . import _lib
+from .fasta import read_fasta, reverse_complement
+from .grna import Target, gRNAHit, gRNAHits
+from .pam import PAM
+
+
+def find_multi_gRNA(target_fname, pam="NGG", gRNA_len=20):
+    """All PAM-adjacent gRNA of length `gRNA_len` in the records of `target_fname`, both strands.
+
+    Hit ranges are forward-strand, 0-based, end-exclusive; `hit_id` counts hits in scan order (record,
+    '+' then '-', ascending start) and sequences are keyed in first-occurrence order, so `gRNA_001...`
+    ids come out exactly as the reference assigns them (generate_grna.py:36-53, grna.py:630-643)."""
+    pam = PAM(pam=pam, gRNA_length=gRNA_len)
+    pam.regex()                                   # echoes "PAM pattern: ..." like the reference (pam.py:124)
+    program = pam.program()
+    hits = gRNAHits()
+    hit_id = 0
+    for rec_id, seq in read_fasta(target_fname):
+        n = len(seq)
+        target = Target(seq, id=rec_id, strand="+")
+        if n < gRNA_len:
+            continue
+        plus, minus = _lib.enumerate_sites(seq, program, gRNA_len)
+        fwd = np.frombuffer(seq.upper().encode("latin-1"), dtype=np.uint8)
+        rvs = np.frombuffer(reverse_complement(seq).upper().encode("latin-1"), dtype=np.uint8)
+        for strand, text, starts in (("+", fwd, plus), ("-", rvs, minus)):
+            if len(starts) == 0:
+                continue
+            windows = np.lib.stride_tricks.sliding_window_view(text, gRNA_len)[starts]
+            keys = windows.copy().view("S%d" % gRNA_len).ravel()
+            for s, key in zip(starts.tolist(), keys.tolist()):
+                a, b = (s, s + gRNA_len) if strand == "+" else (n - s - gRNA_len, n - s)
+                hits.add_hit(key.decode("latin-1"), gRNAHit(target, a, b, strand, hit_id))
+                hit_id += 1
+    return hits

@@ -1,0 +1,217 @@
+"""gRNA containers - the boundary types the reference's grna()/filter_background() produce and consume
+(grna.py:163-1298): Target, gRNAHit, gRNASeq, gRNAHits, with the accessors and writers the hot path and
+its callers use (write_fasta grna.py:1061-1089, write_mapping v5 grna.py:925-1060, set_seqs_check
+grna.py:580-593, assign_seqid grna.py:630-643).  Output text pinned by tests/golden/enumerate.json."""
+
+
+def _status_text(v):
+    return "pass" if v is True else "fail" if v is False else "NA"
+
+
+def _status_value(v):
+    if isinstance(v, str):
+        return True if v == "pass" else False if v == "fail" else None
+    return v
+
+
+class CheckObj:
+    """Named tri-state checks: True/False/None <-> pass/fail/NA (grna.py:28-161)."""
+
+    def __init__(self, *names):
+        self._checks = {n: None for n in names}
+
+    @property
+    def check_names(self):
+        return list(self._checks)
+
+    def set_check(self, name, status):
+        self._checks[name] = _status_value(status)
+
+    def check(self, name, mode="bool"):
+        v = self._checks.get(name)
+        return _status_text(v) if mode == "str" else v
+
+    def check_exists(self, name):
+        return name in self._checks
+
+
+class Target:
+    def __init__(self, seq, id=None, strand=None):
+        self._seq = str(seq).upper()
+        self.id, self.strand = id, strand
+        self.sense = None
+
+    def __len__(self):
+        return len(self._seq)
+
+    def __str__(self):
+        return self._seq
+
+    @property
+    def seq(self):
+        return self._seq
+
+
+class gRNASeq(CheckObj):
+    def __init__(self, seq):
+        super().__init__("background", "GC")
+        self._seq = str(seq).upper()
+        self.id = None
+
+    @property
+    def seq(self):
+        return self._seq
+
+    def __str__(self):
+        return self._seq
+
+
+class gRNAHit(CheckObj):
+    """One occurrence: forward-strand, 0-based, end-exclusive range on its target (grna.py:1144)."""
+
+    def __init__(self, target, start, end, strand, hit_id):
+        super().__init__("background", "GC", "feature", "exclude")
+        self.target, self._range, self.strand, self.hit_id = target, (start, end), strand, hit_id
+        self._parent_sense = None
+
+    @property
+    def target_id(self):
+        return self.target.id
+
+    @property
+    def target_len(self):
+        return len(self.target)
+
+    @property
+    def range(self):
+        return tuple(self._range)
+
+    @property
+    def start(self):
+        return self._range[0]
+
+    @property
+    def end(self):
+        return self._range[1]
+
+    def set_parent_sense(self, sense):
+        self._parent_sense = sense
+
+    def parent_sense(self, mode="raw"):
+        s = self._parent_sense
+        if mode == "str":
+            return "sense" if s in ("+", "sense") else "antisense" if s in ("-", "antisense") else "NA"
+        return s
+
+
+class gRNAHits:
+    """{SEQ: gRNASeq} and {SEQ: [gRNAHit]} in first-occurrence order (grna.py:252-1118)."""
+
+    def __init__(self):
+        self._gRNAseqs, self._hits = {}, {}
+
+    def __len__(self):
+        return len(self._gRNAseqs)
+
+    def __repr__(self):
+        return "gRNAHits(gRNA = %d)" % len(self)
+
+    @property
+    def gRNAseqs(self):
+        return self._gRNAseqs
+
+    @property
+    def hits(self):
+        return self._hits
+
+    @property
+    def seqs(self):
+        return list(self._gRNAseqs)
+
+    def add_hit(self, seq, hit):
+        seq = str(seq).upper()
+        if seq not in self._gRNAseqs:
+            self._gRNAseqs[seq] = gRNASeq(seq)
+            self._hits[seq] = []
+        self._hits[seq].append(hit)
+
+    def get_hits(self, seq):
+        return self._hits[str(seq).upper()]
+
+    def get_gRNAseq_by_seq(self, seq):
+        return self._gRNAseqs.get(str(seq).upper())
+
+    def get_gRNAseq_by_id(self, gid):
+        for s in self._gRNAseqs.values():
+            if s.id == gid:
+                return s
+        return None
+
+    def flatten_gRNAseqs(self):
+        return list(self._gRNAseqs.values())
+
+    def flatten_hits(self):
+        return [h for hs in self._hits.values() for h in hs]
+
+    def assign_seqid(self, prefix="gRNA_", zfill=3, assign_all=True):
+        for i, s in enumerate(self._gRNAseqs.values()):
+            if s.id is None or assign_all:
+                s.id = "%s%s" % (prefix, str(i + 1).zfill(zfill))
+
+    def set_seqs_check(self, check_name, status, seqs):
+        for seq in seqs:
+            s = self.get_gRNAseq_by_seq(seq)
+            if s is not None:
+                s.set_check(check_name, status)
+
+    def filter_seqs(self, *check_names, accept_invalid=False):
+        """Sequences passing every named sequence-level check (grna.py:820-866, subset used by the path)."""
+        out = []
+        for s in self._gRNAseqs.values():
+            vals = [s.check(n) for n in check_names]
+            if all(v is True or (accept_invalid and v is None) for v in vals):
+                out.append(s.seq)
+        return out
+
+    # -- writers ---------------------------------------------------------------------------------
+    def write_fasta(self, fout, ids=(), seqs=(), write_all=False):
+        if write_all:
+            chosen = self.flatten_gRNAseqs()
+        elif seqs:
+            chosen = [self.get_gRNAseq_by_seq(s) for s in seqs if self.get_gRNAseq_by_seq(s) is not None]
+        elif ids:
+            chosen = [s for s in (self.get_gRNAseq_by_id(i) for i in ids) if s is not None]
+        else:
+            open(fout, "w").close()
+            return
+        self.assign_seqid(assign_all=False)
+        with open(fout, "w") as fh:
+            for s in chosen:
+                fh.write(">%s\n" % s.id)
+                for i in range(0, len(s.seq), 60):
+                    fh.write(s.seq[i:i + 60] + "\n")
+
+    def write_mapping(self, fout, sets=(), write_all=False, write_checks=False,
+                      checks=("background", "GC", "feature")):
+        """MINORg .map version 5: 1-based inclusive start/end; stable sorts by start, target id, gRNA id, set."""
+        checks = list(checks) if write_checks else []
+        groups = [list(s) for s in sets] if sets else ([self.seqs] if write_all else None)
+        if groups is None:
+            open(fout, "w").close()
+            return
+        header = ["gRNA id", "gRNA sequence", "target id", "target length", "target sense", "gRNA strand",
+                  "start", "end", "set"] + checks
+        rows = []
+        for set_no, members in enumerate(groups, 1):
+            for seq in members:
+                s = self.get_gRNAseq_by_seq(seq)
+                for h in self.get_hits(seq):
+                    a, b = h.range
+                    rows.append([s.id, s.seq, h.target_id, h.target_len, h.parent_sense(mode="str"), h.strand,
+                                 a + 1, b, set_no] +
+                                [(s if c in ("GC", "background") else h).check(c, mode="str") for c in checks])
+        for col in (6, 2, 0, 8):
+            rows.sort(key=lambda r, c=col: r[c])
+        with open(fout, "w") as fh:
+            for r in [header] + rows:
+                fh.write("\t".join(map(str, r)) + "\n")

@@ -1,0 +1,241 @@
+"""Off-target pattern expressions - host-side mirror of the reference's `minorg.ot_regex`
+(`ot_range` ot_regex.py:63-122, `OffTargetExpression` ot_regex.py:124-356): same names, same accept/reject
+behaviour, same left-to-right (no precedence) semantics - parsed into a small tree that is (a) evaluable on
+the host on any object exposing `_num_char_in_range` like the reference's BlastHSP, and (b) lowered to the
+postfix unit program of `mg_criteria` that the device verifier executes on every candidate alignment.
+
+Behaviour pinned by tests/golden/ot_range.json and ot_pattern.json (produced by executing the reference)."""
+import re
+
+from . import _lib
+
+
+class MINORgError(Exception):
+    """Same role as minorg.MINORgError (minorg/__init__.py)."""
+
+
+CHAR_UNALIGNED, CHAR_DEL, CHAR_INS, CHAR_MISMATCH, CHAR_MATCH, CHAR_GAP = " ", "d", "i", "m", ".", "g"
+
+_HEAD = re.compile(r"-*\d+")
+_TAIL = re.compile(r"-(-*\d+)$")
+
+
+def ot_range(range_pattern):
+    """'5' -> (None, 5); '-5' -> (-5, None); '5-' -> (4, None); '-5-' -> (None, -4); '2-4' -> (1, 4);
+    '-2--4' -> (-4, -1).  The pair is used as a Python slice [start:end] on the per-position alignment
+    tuple.  Zero, mixed signs and anything unparsable raise MINORgError (ot_regex.py:63-122)."""
+    bad = MINORgError("Unable to parse off-target pattern range: %s" % (range_pattern,))
+    head = _HEAD.match(range_pattern or "")
+    if head is None:
+        raise bad
+    first_txt = head.group(0)
+    try:
+        first, negative = int(first_txt), first_txt.startswith("-")
+    except ValueError:          # e.g. '--5'
+        raise bad
+    remainder = range_pattern[len(first_txt):]
+    if first == 0:
+        raise bad
+    if remainder == "":
+        return (first, None) if negative else (None, first)
+    if remainder == "-":
+        if negative:
+            return (None, first + 1 if first < -1 else None)
+        return (first - 1, None)
+    tail = _TAIL.search(range_pattern)
+    if tail is None:
+        raise bad
+    second_txt = tail.group(1)
+    if second_txt.startswith("-") != negative:
+        raise bad
+    try:
+        second = int(second_txt)
+    except ValueError:
+        raise bad
+    if second == 0:
+        raise bad
+    if negative:
+        return (second, first + 1 if first < -1 else None)
+    return (first - 1, second)
+
+
+class _Unit:
+    __slots__ = ("text", "n", "mismatch", "ins", "dele", "gap", "start", "end", "rvs")
+
+    def __init__(self, text):
+        lead = re.match(r"\d+", text)
+        rng = re.search(r"[-\d]+$", text)
+        if lead is None or rng is None:
+            raise MINORgError("Unable to parse off-target pattern: %s" % text)
+        self.text = text
+        self.n = int(lead.group(0))
+        self.mismatch = CHAR_MISMATCH in text
+        self.gap = CHAR_GAP in text
+        self.ins = CHAR_INS in text
+        self.dele = CHAR_DEL in text
+        if self.gap and (self.ins or self.dele):
+            # the reference touches a missing attribute here (ot_regex.py:251) and re-raises (:263-264)
+            raise MINORgError("Unable to parse off-target pattern: %s" % text)
+        try:
+            self.start, self.end = ot_range(rng.group(0))
+        except MINORgError:
+            raise MINORgError("Unable to parse off-target pattern: %s" % text)
+        self.rvs = any(v is not None and v < 0 for v in (self.start, self.end))
+
+    @property
+    def chars(self):
+        return ((CHAR_MISMATCH,) if self.mismatch else ()) + ((CHAR_INS,) if self.ins or self.gap else ()) + \
+               ((CHAR_DEL,) if self.dele or self.gap else ())
+
+
+class OffTargetExpression:
+    """Callable like the reference class: expr(blasthsp) -> True if the hit is problematic."""
+
+    def __init__(self, pattern, unaligned_as_mismatch=True, unaligned_as_gap=False):
+        self.pattern = pattern
+        self.unaligned_as_mismatch = unaligned_as_mismatch
+        self.unaligned_as_gap = unaligned_as_gap
+        self.tree, self.length = self._scan(pattern)
+        self.f = self.evaluate
+
+    def __len__(self):
+        return self.length
+
+    def __call__(self, v):
+        return self.evaluate(v)
+
+    # ---- parsing: one left-to-right pass, operators applied as they are met -------------------
+    def _scan(self, text):
+        tree, pending_op = None, None
+
+        def attach(node):
+            nonlocal tree
+            if tree is None:
+                tree = node
+            elif pending_op in ("and", "or"):
+                tree = (pending_op, tree, node)
+            else:
+                raise MINORgError("self._op must be 'and' or 'or' if self.f is not None")
+        if not isinstance(text, str):
+            raise TypeError("pattern must be str")
+        size = len(text)
+        if size == 0:
+            raise TypeError("empty off-target pattern")     # the reference fails on f(None) at call time
+        unit_from = pos = 0
+        while pos < size:
+            ch = text[pos]
+            if ch == "(":
+                sub, used = self._scan(text[pos + 1:])
+                if sub is None:
+                    raise MINORgError("Unable to parse off-target pattern: %s" % text)
+                attach(sub)
+                unit_from = pos = pos + 1 + used
+            elif ch == "," or ch == "|":
+                if unit_from != pos:
+                    attach(("unit", _Unit(text[unit_from:pos])))
+                pending_op = "and" if ch == "," else "or"
+                pos += 1
+                unit_from = pos
+            elif ch == ")":
+                attach(("unit", _Unit(text[unit_from:pos])))
+                pos += 1
+                break
+            elif pos >= size - 1:
+                attach(("unit", _Unit(text[unit_from:size])))
+                pos += 1
+                break
+            else:
+                pos += 1
+        return tree, pos
+
+    # ---- host evaluation (API parity with the reference object) -------------------------------
+    def _unit_true(self, u, hsp):
+        total = hsp._num_char_in_range(*u.chars, start=u.start, end=u.end, rvs_index=u.rvs)
+        una = hsp._num_char_in_range(CHAR_UNALIGNED, start=u.start, end=u.end, rvs_index=u.rvs)
+        if u.mismatch and self.unaligned_as_mismatch:
+            total += una
+        if (u.ins or u.gap) and self.unaligned_as_gap:
+            total += una
+        return total <= u.n
+
+    def evaluate(self, hsp):
+        def walk(node):
+            if node[0] == "unit":
+                return self._unit_true(node[1], hsp)
+            a = walk(node[1])
+            if node[0] == "and":
+                return a and walk(node[2])
+            return a or walk(node[2])
+        return walk(self.tree)
+
+    # ---- device lowering ----------------------------------------------------------------------
+    def units(self):
+        out = []
+
+        def walk(node):
+            if node[0] == "unit":
+                out.append(node[1])
+            else:
+                walk(node[1])
+                walk(node[2])
+        walk(self.tree)
+        return out
+
+    def lower(self, crit):
+        """Fill units/ops of an `_lib.Criteria` (postfix order)."""
+        units, ops = [], []
+
+        def walk(node):
+            if node[0] == "unit":
+                units.append(node[1])
+                ops.append(len(units) - 1)
+            else:
+                walk(node[1])
+                walk(node[2])
+                ops.append(_lib.MG_OP_AND if node[0] == "and" else _lib.MG_OP_OR)
+        walk(self.tree)
+        if len(units) > _lib.MG_MAX_PATTERN_UNITS or len(ops) > _lib.MG_MAX_PATTERN_OPS:
+            raise MINORgError("off-target pattern too long for the device program")
+        crit.n_units, crit.n_ops = len(units), len(ops)
+        none = _lib.MG_SLICE_NONE
+        for i, u in enumerate(units):
+            d = crit.units[i]
+            d.n = u.n
+            d.chars = (_lib.MG_CH_MISMATCH if u.mismatch else 0) | (_lib.MG_CH_INS if (u.ins or u.gap) else 0) | \
+                      (_lib.MG_CH_DEL if (u.dele or u.gap) else 0)
+            d.start = none if u.start is None else u.start
+            d.end = none if u.end is None else u.end
+            d.rvs = int(u.rvs)
+            d.add_unaligned_m = int(u.mismatch and self.unaligned_as_mismatch)
+            d.add_unaligned_g = int((u.ins or u.gap) and self.unaligned_as_gap)
+        for i, o in enumerate(ops):
+            crit.ops[i] = o
+
+    def clauses(self):
+        """Disjunctive normal form: list of clauses, each a list of units (the tree has only AND/OR)."""
+        def walk(node):
+            if node[0] == "unit":
+                return [[node[1]]]
+            a, b = walk(node[1]), walk(node[2])
+            if node[0] == "or":
+                return a + b
+            return [x + y for x in a for y in b]
+        return walk(self.tree)
+
+
+def make_criteria(ot_mismatch=1, ot_gap=0, ot_pattern=None, ot_unaligned_as_mismatch=True,
+                  ot_unaligned_as_gap=False, ot_pamless=True):
+    """The reference's screen attributes (MINORg.py:686-707) -> `_lib.Criteria`.
+    max_mismatch / max_gap follow MINORg.py:2033-2034."""
+    c = _lib.Criteria()
+    c.max_mismatch = max(1, int(ot_mismatch)) - 1
+    c.max_gap = max(1, int(ot_gap)) - 1
+    if c.max_gap > _lib.MG_MAX_GAPS:
+        raise MINORgError("ot_gap > %d is not supported by the device screen" % (_lib.MG_MAX_GAPS + 1))
+    c.pamless = int(bool(ot_pamless))
+    c.prefilter_edits = -1
+    if ot_pattern is not None:
+        expr = ot_pattern if isinstance(ot_pattern, OffTargetExpression) else \
+            OffTargetExpression(ot_pattern, ot_unaligned_as_mismatch, ot_unaligned_as_gap)
+        expr.lower(c)
+    return c

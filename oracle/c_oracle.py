@@ -1,0 +1,55 @@
+"""ctypes loader of the C oracle (oracle/screen_oracle.c).  Test infrastructure only - see the header of
+screen_oracle.c.  Used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libscreen_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "screen_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        # -march=native is avoided: the .so built in the authoring container travels to the GPU box
+        subprocess.check_call(["gcc", "-O3", "-mpopcnt", "-shared", "-fPIC", "-pthread", src, "-o", _SO])
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def screen_hamming(contigs, masks, grnas, max_mismatch, threads=1):
+    """contigs: [(name, seq)], masks: [(contig index, start, end)], grnas: [str] -> uint32 counts per gRNA."""
+    bufs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
+    offsets = np.zeros(len(bufs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bufs], out=offsets[1:])
+    blob = np.frombuffer(b"".join(bufs) or b"\0", dtype=np.uint8)
+    return screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads)
+
+
+def screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads=1):
+    masks = list(masks)
+    mc = np.array([m[0] for m in masks] or [0], dtype=np.int32)
+    ms = np.array([m[1] for m in masks] or [0], dtype=np.int64)
+    me = np.array([m[2] for m in masks] or [0], dtype=np.int64)
+    g = [s.encode() if isinstance(s, str) else bytes(s) for s in grnas]
+    L = len(g[0]) if g else 1
+    gb = np.frombuffer(b"".join(g) or b"\0", dtype=np.uint8)
+    out = np.zeros(max(1, len(g)), dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _load().oracle_screen_hamming(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
+                                       C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
+                                       C.c_int(threads), p(out))
+    if rc != 0:
+        raise RuntimeError("oracle_screen_hamming failed: %d" % rc)
+    return out[:len(g)]

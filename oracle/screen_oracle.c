@@ -1,0 +1,123 @@
+/* CPU ORACLE (test infrastructure, NOT product code) - C restatement of the exhaustive ungapped screen.
+ *
+ * Same semantics as oracle/minorg_oracle.py:screen_hamming, i.e. reduction (2) of SURVEY.md 8c of the
+ * reference's criterion MINORg._is_offtarget_aln_nopattern (minorg/MINORg.py:2018-2044) with ot_gap<=1,
+ * ot_pamless, no pattern, applied to EVERY window instead of BLAST's HSPs, plus the position check
+ * MINORg._is_offtarget_pos (MINORg.py:1994-2000; functions.py:310-325):
+ *   a window (contig, start p in [-L+1, n), strand) counts for gRNA q iff
+ *     #{positions off the contig} + #{on-contig positions where q and the subject differ or either is not
+ *     ACGT} <= max_mismatch, and its on-contig span is not inside one masked interval.
+ * Parity pinning: tests/test_oracle_c.py checks this file against the Python oracle on the golden screen
+ * cases (whose verdicts come from the reference's own predicates).
+ *
+ * Also the "port" CPU baseline timed by bench.py: 2-bit windows, 64-bit XOR + popcount, pthreads over
+ * window ranges.   Build: gcc -O3 -march=native -shared -fPIC -pthread screen_oracle.c -o libscreen_oracle.so
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static inline int code_of(char c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+typedef struct {
+    const uint8_t* codes; /* contig codes, 0..3 / 4 */
+    int64_t n;            /* contig length */
+    int64_t p0, p1;       /* window starts [p0, p1) handled by this thread */
+    const uint64_t* qbits; /* [nq] 2-bit packed queries */
+    const uint64_t* qinv;  /* [nq] invalid positions of each query at the even bits */
+    int nq, L, max_mm;
+    const int64_t* ms; const int64_t* me; int n_masks; /* masks of this contig */
+    uint32_t* counts;     /* [nq] thread-private */
+} job_t;
+
+static int span_masked(const job_t* j, int64_t a, int64_t b) {
+    for (int i = 0; i < j->n_masks; ++i) {
+        int64_t lo = j->ms[i] < j->me[i] ? j->ms[i] : j->me[i];
+        int64_t hi = j->ms[i] < j->me[i] ? j->me[i] : j->ms[i];
+        if (a >= lo && b <= hi) return 1;
+    }
+    return 0;
+}
+
+static void* run(void* arg) {
+    job_t* j = (job_t*)arg;
+    const int L = j->L;
+    const uint64_t even = 0x5555555555555555ULL;
+    const uint64_t lmask = (L >= 32) ? even : (((1ULL << (2 * L)) - 1) & even);
+    for (int64_t p = j->p0; p < j->p1; ++p) {
+        uint64_t w = 0, winv = 0;
+        for (int k = 0; k < L; ++k) {
+            const int64_t i = p + k;
+            const int c = (i < 0 || i >= j->n) ? 4 : j->codes[i];
+            if (c == 4) winv |= 1ULL << (2 * k); else w |= (uint64_t)c << (2 * k);
+        }
+        int masked = -1;
+        for (int q = 0; q < j->nq; ++q) {
+            const uint64_t x = w ^ j->qbits[q];
+            const uint64_t d = ((x | (x >> 1)) & lmask) | winv | j->qinv[q];
+            if (__builtin_popcountll(d) > j->max_mm) continue;
+            if (masked < 0) {
+                const int64_t a = p < 0 ? 0 : p, b = (p + L > j->n) ? j->n : p + L;
+                masked = (a >= b) ? 1 : span_masked(j, a, b);
+            }
+            if (!masked) j->counts[q]++;
+        }
+    }
+    return NULL;
+}
+
+/* counts_out[i] = number of (window, strand) pairs within budget and outside masks, over all contigs. */
+int oracle_screen_hamming(const char* seq, const int64_t* offsets, int n_contigs,
+                          const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                          const char* grna, int n, int L, int max_mm, int n_threads, uint32_t* counts_out) {
+    if (L < 1 || L > 32 || n < 0 || n_threads < 1) return -2;
+    const int nq = 2 * n;
+    uint64_t* qbits = (uint64_t*)calloc((size_t)nq + 1, 8);
+    uint64_t* qinv = (uint64_t*)calloc((size_t)nq + 1, 8);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < L; ++k) {
+            const int c = code_of(grna[(size_t)i * L + k]);
+            if (c == 4) { qinv[i] |= 1ULL << (2 * k); qinv[n + i] |= 1ULL << (2 * (L - 1 - k)); }
+            else { qbits[i] |= (uint64_t)c << (2 * k); qbits[n + i] |= (uint64_t)(3 - c) << (2 * (L - 1 - k)); }
+        }
+    }
+    memset(counts_out, 0, sizeof(uint32_t) * (size_t)n);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    job_t* jobs = (job_t*)malloc(sizeof(job_t) * (size_t)n_threads);
+    uint32_t* priv = (uint32_t*)calloc((size_t)n_threads * (size_t)(nq + 1), 4);
+    for (int c = 0; c < n_contigs; ++c) {
+        const int64_t len = offsets[c + 1] - offsets[c];
+        uint8_t* codes = (uint8_t*)malloc((size_t)len + 1);
+        for (int64_t i = 0; i < len; ++i) codes[i] = (uint8_t)code_of(seq[offsets[c] + i]);
+        int nm = 0;
+        int64_t* ms = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
+        int64_t* me = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
+        for (int i = 0; i < n_masks; ++i) if (mask_contig[i] == c) { ms[nm] = mask_start[i]; me[nm] = mask_end[i]; ++nm; }
+        const int64_t first = -(int64_t)L + 1, last = len; /* window starts [first, last) */
+        const int64_t total = last - first;
+        for (int t = 0; t < n_threads; ++t) {
+            job_t* j = &jobs[t];
+            j->codes = codes; j->n = len; j->qbits = qbits; j->qinv = qinv; j->nq = nq; j->L = L; j->max_mm = max_mm;
+            j->ms = ms; j->me = me; j->n_masks = nm; j->counts = priv + (size_t)t * (size_t)(nq + 1);
+            j->p0 = first + total * t / n_threads;
+            j->p1 = first + total * (t + 1) / n_threads;
+            pthread_create(&th[t], NULL, run, j);
+        }
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+        free(codes); free(ms); free(me);
+    }
+    for (int t = 0; t < n_threads; ++t)
+        for (int i = 0; i < n; ++i)
+            counts_out[i] += priv[(size_t)t * (size_t)(nq + 1) + i] + priv[(size_t)t * (size_t)(nq + 1) + n + i];
+    free(priv); free(jobs); free(th); free(qbits); free(qinv);
+    return 0;
+}

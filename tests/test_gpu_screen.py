@@ -1,0 +1,173 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+libminorg_b200.so (ctypes); results are compared with the CPU oracle on the same inputs."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, minorg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from minorg_b200 import _lib
+    assert _lib.device_count() > 0, "no CUDA device"
+    name, sms = _lib.init(0)
+    print("device:", name, sms, "SMs")
+    return _lib
+
+
+def _random_contig(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def test_pack_roundtrip(L):
+    rng = random.Random(1)
+    contigs = [("a", _random_contig(rng, 1000, "ACGTacgtNRY")), ("b", _random_contig(rng, 31)), ("c", ""),
+               ("d", _random_contig(rng, 5)), ("e", _random_contig(rng, 4097, "ACGTn"))]
+    g = L.Genome.from_contigs(contigs)
+    assert g.n_contigs == 5 and g.total_bases == sum(len(s) for _, s in contigs)
+    for i, (_, s) in enumerate(contigs):
+        assert g.contig_length(i) == len(s)
+        want = "".join(c.upper() if c in "ACGTacgt" else "N" for c in s)
+        assert g.decode(i, 0, len(s)) == want
+    g.free()
+
+
+def _hamming_via_abi(L, contigs, masks, grnas, M):
+    from minorg_b200.ot_regex import make_criteria
+    blob = np.frombuffer("".join(s for _, s in contigs).encode() or b"\0", dtype=np.uint8)
+    offsets = np.zeros(len(contigs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for _, s in contigs], out=offsets[1:])
+    gb = np.frombuffer("".join(grnas).encode(), dtype=np.uint8)
+    crit = make_criteria(ot_mismatch=M + 1, ot_gap=0)
+    return L.screen_host(blob, offsets, masks, gb, len(grnas), len(grnas[0]), crit, None)
+
+
+def test_hamming_golden_cases(L, golden):
+    n = 0
+    for c in golden("screen_cases.json")["cases"]:
+        k = c["criteria"]
+        if k.get("pattern") is not None or not k["pamless"] or k["ot_gap"] > 1:
+            continue
+        M = max(1, k["ot_mismatch"]) - 1
+        contigs = [tuple(x) for x in c["contigs"]]
+        names = [x[0] for x in contigs]
+        masks = [(names.index(m[1]), m[2], m[3]) for m in c["masks"]]
+        got = _hamming_via_abi(L, contigs, masks, c["grnas"], M)
+        want = O.screen_hamming(c["grnas"], contigs, c["masks"], M)
+        assert got.tolist() == want, c["name"]
+        assert [x > 0 for x in got.tolist()] == c["fail"], c["name"]     # verdicts of the reference's predicates
+        n += 1
+    assert n >= 7
+
+
+@pytest.mark.parametrize("glen,M,seed", [(20, 0, 1), (20, 1, 2), (20, 2, 3), (20, 4, 4), (23, 3, 5), (12, 1, 6),
+                                         (32, 5, 7), (17, 6, 8), (1, 0, 9), (20, 7, 10)])
+def test_hamming_random_vs_c_oracle(L, glen, M, seed):
+    rng = random.Random(seed)
+    contigs = [("chr%d" % i, _random_contig(rng, rng.choice([70000, 3000, 17, 40000]), "ACGT" * 8 + "Nacgt"))
+               for i in range(4)]
+    grnas = []
+    for i in range(300):
+        _, seq = contigs[rng.randrange(len(contigs))]
+        if len(seq) > glen + 4 and i % 3:
+            p = rng.randrange(0, len(seq) - glen)
+            g = list(seq[p:p + glen].upper().replace("N", "A"))
+            for _ in range(rng.randrange(0, M + 3)):
+                g[rng.randrange(glen)] = rng.choice("ACGT")
+            g = "".join(g)
+            grnas.append(O.reverse_complement(g) if rng.random() < 0.5 else g)
+        else:
+            grnas.append(_random_contig(rng, glen, "ACGT" * 6 + "N"))
+    masks = [(0, 100, 400), (0, 350, 900), (1, 0, 3000), (3, 39990, 40000), (0, 69990, 70000)]
+    masks = [m for m in masks if m[2] <= len(contigs[m[0]][1])]
+    if M >= glen:
+        M = glen - 1
+    got = _hamming_via_abi(L, contigs, masks, grnas, M)
+    want = c_oracle.screen_hamming(contigs, masks, grnas, M, threads=8)
+    assert np.array_equal(got, want)
+    assert (got > 0).any() and (got == 0).any() or glen <= 12 or M >= 5
+
+
+def test_resident_api_and_sharding(L):
+    """mg_screen on resident handles; shards of the window range add up to the whole (multi-GPU split)."""
+    import torch
+    from minorg_b200.ot_regex import make_criteria
+    rng = random.Random(11)
+    contigs = [("x", _random_contig(rng, 50000)), ("y", _random_contig(rng, 20000))]
+    grnas = [contigs[0][1][i * 97:i * 97 + 20] for i in range(64)] + [_random_contig(rng, 20) for _ in range(37)]
+    g = L.Genome.from_contigs(contigs)
+    g.set_masks([(0, 0, 2000)])
+    q = L.Queries(grnas)
+    crit = make_criteria(ot_mismatch=3, ot_gap=0)
+    whole = torch.zeros(2 * len(grnas), dtype=torch.int32, device="cuda")
+    L.screen(g, q, crit, None, whole.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    parts = torch.zeros_like(whole)
+    glen = g.global_length
+    cuts = [0, glen // 3, glen // 3 + 7, 2 * glen // 3, glen]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        L.screen(g, q, crit, None, parts.data_ptr(), win_begin=a, win_end=b, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
+    n = len(grnas)
+    got = (whole[:n] + whole[n:]).cpu().numpy().astype(np.uint32)
+    want = c_oracle.screen_hamming(contigs, [(0, 0, 2000)], grnas, 2, threads=4)
+    assert np.array_equal(got, want)
+    q.free()
+    g.free()
+
+
+def test_many_queries_multiple_chunks(L):
+    """More query groups than fit one shared-memory chunk (exercises the chunk loop)."""
+    rng = random.Random(12)
+    contigs = [("x", _random_contig(rng, 3000))]
+    grnas = [_random_contig(rng, 20) for _ in range(13000)]
+    for i in range(0, 13000, 7):
+        p = rng.randrange(0, 2980)
+        grnas[i] = contigs[0][1][p:p + 20]
+    got = _hamming_via_abi(L, contigs, [], grnas, 1)
+    want = c_oracle.screen_hamming(contigs, [], grnas, 1, threads=8)
+    assert np.array_equal(got, want)
+
+
+def test_enumeration_matches_reference_vectors(L, golden, tmp_path):
+    from minorg_b200.generate_grna import find_multi_gRNA
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for r in golden("enumerate.json")["rows"]:
+        h = find_multi_gRNA(os.path.join(gdir, r["fasta"]), pam=r["pam"], gRNA_len=r["L"])
+        assert len(h) == r["n_seqs"], (r["fasta"], r["pam"], r["L"])
+        assert len(h.flatten_hits()) == r["n_hits"]
+        if "hits" in r:
+            got = [[s, [[x.target_id, x.range[0], x.range[1], x.strand, x.hit_id, x.target_len] for x in h.get_hits(s)]]
+                   for s in h.seqs]
+            assert got == r["hits"], (r["fasta"], r["pam"], r["L"])
+        if "fasta_text" in r:
+            fa, mp = str(tmp_path / "g.fasta"), str(tmp_path / "g.map")
+            h.write_fasta(fa, write_all=True)
+            h.write_mapping(mp, write_all=True, write_checks=True)
+            assert open(fa).read() == r["fasta_text"]
+            assert open(mp).read() == r["map_text"]
+
+
+def test_mask_find_vs_oracle(L):
+    rng = random.Random(13)
+    t1, t2, t3 = _random_contig(rng, 700), _random_contig(rng, 45), "ACGTACGT"
+    contigs = [("c0", _random_contig(rng, 5000) + t1 + _random_contig(rng, 300) + O.reverse_complement(t1).lower()),
+               ("c1", t2 + _random_contig(rng, 2000) + t2 + "N" + t1[:699]),
+               ("c2", "ACGTACGTACGT" + t3)]
+    seqs = [("t1", t1), ("t2", t2), ("t3", t3), ("absent", _random_contig(rng, 60))]
+    g = L.Genome.from_contigs(contigs)
+    got = g.find_exact([s for _, s in seqs])
+    names = [c[0] for c in contigs]
+    got_set = {(seqs[a][0], names[b], c, d) for a, b, c, d, _ in got}
+    assert got_set == O.find_masks(seqs, contigs)
+    assert len(got_set) >= 6
+    g.free()
+
+
+def test_microbench_runs(L):
+    assert L.microbench(0) > 1000 and L.microbench(1) > 500

@@ -1,0 +1,88 @@
+"""Host-side mirrors of the reference interface (minorg_b200.pam / ot_regex) against the golden vectors
+produced by executing the reference classes.  No GPU and no compute calls into the shared library."""
+import pytest
+
+from minorg_b200 import ot_regex as R
+from minorg_b200.pam import PAM, PAM_PATTERNS
+from oracle import minorg_oracle as O
+
+
+def test_pam_mirror(golden, capsys):
+    d = golden("pam.json")
+    for r in d["rows"]:
+        if "error" in r:
+            with pytest.raises(Exception):
+                PAM(r["pam"], r["L"]).regex()
+            continue
+        p = PAM(r["pam"], r["L"])
+        assert p.pam == r["parsed"] and repr(p) == r["parsed"]
+        assert p.regex().pattern == r["regex"]
+        assert (p.five_prime(), p.three_prime()) == (r["five"], r["three"])
+        assert (p.five_prime_maxlen(), p.three_prime_maxlen()) == (r["five_max"], r["three_max"])
+    assert "PAM pattern: .{20}(?=[GATC]GG)" in capsys.readouterr().out      # pam.py:124 prints
+    src = PAM("TTTV.", 23)
+    for c in d["copy_ctor"]:
+        assert PAM(src, c["arg_L"]).gRNA_length == c["got_L"]
+    assert PAM_PATTERNS["Cas12a"] == "TTTV." and PAM_PATTERNS["spcas9"] == ".NGG"
+
+
+def test_pam_program_lowering():
+    p = PAM("R{1,2}T", 20).program()
+    assert p.five.n_alts == 0 and p.three.n_alts == 2 and p.three_maxlen == 9
+    assert sorted(p.three.len[i] for i in range(2)) == [3, 4]
+    q = PAM("TTTV.", 23).program()
+    assert q.five.n_alts == 1 and q.five.len[0] == 4 and q.three.n_alts == 0 and q.five_maxlen == 4
+    assert q.five.allow4[0][3] == 0b0111 and q.five.allow4[0][0] == 0b1000
+    assert (q.five.allow[0][0][ord("t") >> 5] >> (ord("t") & 31)) & 1
+
+
+def test_ot_range_mirror(golden):
+    for r in golden("ot_range.json")["rows"]:
+        if r.get("error"):
+            with pytest.raises(R.MINORgError):
+                R.ot_range(r["range"])
+        else:
+            assert list(R.ot_range(r["range"])) == r["out"], r
+
+
+class _HSP:
+    """What the reference's BlastHSP offers to OffTargetExpression (blast.py:151-172)."""
+
+    def __init__(self, aln):
+        self.aln = aln
+
+    def _num_char_in_range(self, *chars, start=None, end=None, rvs_index=False):
+        return self.aln.count(chars, start, end, rvs_index)
+
+
+def test_pattern_mirror(golden):
+    d = golden("ot_pattern.json")
+    n = 0
+    for a in d["rows"]:
+        hsp = _HSP(O.Alignment.from_btop(a["btop"], a["qstart"], a["qend"], a["qlen"]))
+        for key, want in a["results"].items():
+            pat, flags = key.rsplit("|", 1)
+            uam, uag = flags[0] == "1", flags[1] == "1"
+            if isinstance(want, str):
+                with pytest.raises(Exception):
+                    R.OffTargetExpression(pat, uam, uag)(hsp)
+            else:
+                assert R.OffTargetExpression(pat, uam, uag)(hsp) == want, key
+                n += 1
+    assert n > 5000
+    hsp = _HSP(O.Alignment.from_btop("20", 0, 20, 20))
+    for pat, want in d["odd_patterns"].items():
+        if isinstance(want, str):
+            with pytest.raises(Exception):
+                R.OffTargetExpression(pat)(hsp)
+        else:
+            assert R.OffTargetExpression(pat)(hsp) == want, pat
+
+
+def test_criteria_lowering():
+    c = R.make_criteria(ot_mismatch=5, ot_gap=2, ot_pattern="(0mg5,1mg6-)|2m-4--2", ot_pamless=False)
+    assert (c.max_mismatch, c.max_gap, c.pamless, c.n_units, c.n_ops) == (4, 1, 0, 3, 5)
+    assert [c.ops[i] for i in range(5)] == [0, 1, -1, 2, -2]
+    assert (c.units[2].start, c.units[2].end, c.units[2].rvs, c.units[2].n) == (-2, -3, 1, 2)
+    assert c.units[1].start == 5 and c.units[1].end == -(2 ** 31)
+    assert R.make_criteria(0, 0).max_mismatch == 0 and R.make_criteria(1, 1).max_gap == 0
