@@ -19,6 +19,7 @@
 // once per query chunk (0.375 B/base) and is three orders of magnitude below the HBM roofline.
 #include "common.cuh"
 #include "csa_gen.cuh"
+#include "verify.cuh"
 
 namespace mg {
 
@@ -62,10 +63,27 @@ __device__ __noinline__ void report_hits(const GenomeView& gv, int n_queries, in
     }
 }
 
-template <int L, int K, int THREADS>
+// Cold path of the general screen: the Hamming budget is only a prefilter; each survivor is an anchor for the
+// exact verifier (verify.cuh).  Query q < N is gRNA q on the '+' strand, q >= N its reverse complement, i.e.
+// gRNA q-N on the '-' strand, whose window [p, p+L) ends at glen - p in reverse-complement coordinates.
+__device__ __noinline__ void verify_hits(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* ctx, uint32_t hit,
+                                         int group, int64_t p, uint32_t* __restrict__ counts) {
+    while (hit) {
+        const int i = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const int q = group * 32 + i;
+        if (q >= 2 * qv.n) continue;
+        const int gi = q < qv.n ? q : q - qv.n;
+        const int strand = q < qv.n ? 1 : -1;
+        const int64_t e = strand > 0 ? p + qv.len : gv.glen - p;
+        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * qv.len, strand, e)) atomicAdd(counts + q, 1u);
+    }
+}
+
+template <int L, int K, int THREADS, bool GENERAL>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chunk, int64_t wb, int64_t we,
-                        uint32_t* __restrict__ counts) {
+                        uint32_t* __restrict__ counts, const GeneralCtx* __restrict__ gctx) {
     constexpr int S = 4 * L + 1;                     // table words per group
     constexpr int NB = mgcsa::CountBits<L>::value;
     extern __shared__ uint32_t tab[];
@@ -108,15 +126,18 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
                 uint32_t bits[NB];
                 mgcsa::csa_count<L>(x, bits);
                 const uint32_t hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
-                if (hit) report_hits(gv, 2 * qv.n, L, hit, cg + g, p, counts);
+                if (hit) {
+                    if (GENERAL) verify_hits(gv, qv, gctx, hit, cg + g, p, counts);
+                    else report_hits(gv, 2 * qv.n, L, hit, cg + g, p, counts);
+                }
             }
         }
     }
 }
 
-template <int L, int K>
+template <int L, int K, bool GENERAL = false>
 static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t wb, int64_t we, uint32_t* d_counts,
-                      cudaStream_t s) {
+                      cudaStream_t s, const GeneralCtx* gctx = nullptr) {
     constexpr int THREADS = 1024;
     constexpr int S = 4 * L + 1;
     int dev = 0, sms = 0, smem_max = 0;
@@ -126,13 +147,13 @@ static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t
     const int max_groups = (smem_max - 1024) / (S * 4);
     const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
     const size_t smem = (size_t)gpc * S * 4;
-    auto kern = screen_bitsliced_kernel<L, K, THREADS>;
+    auto kern = screen_bitsliced_kernel<L, K, THREADS, GENERAL>;
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nwin = we - wb;
     int64_t grid = (nwin + THREADS - 1) / THREADS;
     if (grid > sms) grid = sms;             // persistent: one CTA per SM, each owns a contiguous genome slice
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts);
+    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts, gctx);
     MG_CUDA(cudaGetLastError());
     return MG_OK;
 }
@@ -165,6 +186,23 @@ int launch_screen_bitsliced(const mg_genome* g, const mg_queries* q, int max_mis
         MG_CASE_RT(32)
 #undef MG_CASE_FULL
 #undef MG_CASE_RT
+        default: set_error("gRNA length %d unsupported (1..32)", q->len); return MG_ERR_UNSUPPORTED;
+    }
+}
+
+
+// Same scan as a prefilter for the general screen (runtime budget, cold path = exact verifier).
+int launch_screen_bitsliced_general(const mg_genome* g, const mg_queries* q, int k, const GeneralCtx* d_ctx,
+                                    int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s) {
+    if (q->n == 0 || we <= wb) return MG_OK;
+    switch (q->len) {
+#define MG_CASE_GEN(LL) case LL: return launch_one<LL, -1, true>(g, q, k, wb, we, d_counts, s, d_ctx);
+        MG_CASE_GEN(1) MG_CASE_GEN(2) MG_CASE_GEN(3) MG_CASE_GEN(4) MG_CASE_GEN(5) MG_CASE_GEN(6) MG_CASE_GEN(7) MG_CASE_GEN(8)
+        MG_CASE_GEN(9) MG_CASE_GEN(10) MG_CASE_GEN(11) MG_CASE_GEN(12) MG_CASE_GEN(13) MG_CASE_GEN(14) MG_CASE_GEN(15)
+        MG_CASE_GEN(16) MG_CASE_GEN(17) MG_CASE_GEN(18) MG_CASE_GEN(19) MG_CASE_GEN(20) MG_CASE_GEN(21) MG_CASE_GEN(22)
+        MG_CASE_GEN(23) MG_CASE_GEN(24) MG_CASE_GEN(25) MG_CASE_GEN(26) MG_CASE_GEN(27) MG_CASE_GEN(28) MG_CASE_GEN(29)
+        MG_CASE_GEN(30) MG_CASE_GEN(31) MG_CASE_GEN(32)
+#undef MG_CASE_GEN
         default: set_error("gRNA length %d unsupported (1..32)", q->len); return MG_ERR_UNSUPPORTED;
     }
 }

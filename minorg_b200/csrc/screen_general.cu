@@ -1,9 +1,166 @@
-// K4a/K5: general screen (patterns, gaps, PAM proximity).  Placeholder until the verifier lands.
+// K4a/K5: the general screen - off-target patterns, gaps, PAM proximity - as prefilter + exact verifier.
+//
+// Replaces MINORg._offtarget_hits for every criterion the reference offers (MINORg.py:2015-2102):
+//   prefilter  (a NECESSARY condition, evaluated for every cell)
+//     * no gaps allowed : the bit-sliced Hamming scan of screen_bitsliced.cu with budget K (cold path = verifier)
+//     * gaps allowed    : Myers' bit-parallel <=K-edit search (one 32-bit column per text character)
+//     * no finite K     : every cell goes to the verifier (degenerate patterns; small inputs)
+//   verifier   verify.cuh: exact enumeration of the alignment universe at the surviving anchors.
+// K = max_mismatch + max_gap without a pattern (MINORg.py:2037-2038: unaligned positions and gaps spend one
+// combined budget), or the bound the host derives from the pattern (ot_regex.OffTargetExpression.edit_bound).
 #include "common.cuh"
+#include "verify.cuh"
+
 namespace mg {
-int launch_screen_general(const mg_genome*, const mg_queries*, const mg_criteria*, const mg_pam*, int64_t, int64_t,
-                          uint32_t*, cudaStream_t) {
-    set_error("general screen (pattern / gaps / PAM proximity) not built yet");
-    return MG_ERR_UNSUPPORTED;
+
+int launch_screen_bitsliced_general(const mg_genome* g, const mg_queries* q, int k, const GeneralCtx* d_ctx,
+                                    int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s);
+
+// ----------------------------------------------------------------------------------------- Myers <= K
+constexpr int kMyersThreads = 128;     // gRNA per CTA (one per thread; a warp shares the text character)
+constexpr int kMyersChunk = 8192;      // text characters per CTA (plus L+K warm-up)
+
+__global__ void __launch_bounds__(kMyersThreads)
+myers_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, int K, int strand, int64_t eb,
+             int64_t ee, uint32_t* __restrict__ counts) {
+    // strand coordinates: anchor e (virtual end, exclusive) in [eb, ee); text position pos = e - 1
+    __shared__ uint8_t text[kMyersChunk + 2 * MG_MAX_GRNA_LEN + 16];
+    __shared__ uint32_t peq[5][kMyersThreads];
+    const int L = qv.len, N = qv.n;
+    const int gi = blockIdx.y * kMyersThreads + threadIdx.x;
+    const int64_t p0 = eb - 1 + (int64_t)blockIdx.x * kMyersChunk;      // first reported text position
+    const int64_t p1 = min(ee - 1, p0 + kMyersChunk);                   // one past the last
+    if (p0 >= p1) return;
+    const int warm = L + K;
+    const int64_t from = p0 - warm;
+    const int n_text = (int)(p1 - from);
+    for (int i = threadIdx.x; i < n_text; i += kMyersThreads) text[i] = (uint8_t)tbase(gv, strand, from + i);
+    {
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        if (gi < N) {
+            const uint8_t* q = qv.codes + (size_t)gi * L;     // gRNA orientation (first N rows)
+            for (int j = 0; j < L; ++j) {
+                const uint32_t b = 1u << j;
+                const int c = q[j];
+                e0 |= c == 0 ? b : 0u; e1 |= c == 1 ? b : 0u; e2 |= c == 2 ? b : 0u; e3 |= c == 3 ? b : 0u;
+            }
+        }
+        peq[0][threadIdx.x] = e0; peq[1][threadIdx.x] = e1; peq[2][threadIdx.x] = e2; peq[3][threadIdx.x] = e3;
+        peq[4][threadIdx.x] = 0u;                            // invalid base: matches nothing
+    }
+    __syncthreads();
+    if (gi >= N) return;
+    const uint32_t top = 1u << (L - 1);
+    uint32_t Pv = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u), Mv = 0u;
+    int score = L;
+    for (int i = 0; i < n_text; ++i) {
+        const uint32_t Eq = peq[text[i]][threadIdx.x];
+        const uint32_t Xv = Eq | Mv;
+        const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        uint32_t Ph = Mv | ~(Xh | Pv);
+        uint32_t Mh = Pv & Xh;
+        score += (Ph & top) ? 1 : 0;
+        score -= (Mh & top) ? 1 : 0;
+        Ph <<= 1;
+        Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        if (score <= K && i >= warm) {
+            const int64_t e = from + i + 1;
+            if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, strand, e))
+                atomicAdd(counts + (strand > 0 ? gi : N + gi), 1u);
+        }
+    }
 }
+
+// ----------------------------------------------------------------------------------------- every cell
+__global__ void __launch_bounds__(128)
+allcells_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, int strand, int64_t eb, int64_t ee,
+                uint32_t* __restrict__ counts) {
+    const int L = qv.len, N = qv.n;
+    const int64_t n_anchor = ee - eb;
+    const int64_t total = n_anchor * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = eb + idx % n_anchor;
+        const int gi = (int)(idx / n_anchor);
+        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, strand, e))
+            atomicAdd(counts + (strand > 0 ? gi : N + gi), 1u);
+    }
+}
+
+static void fill_side(const mg_pam_side& in, PamSideDev& out) {
+    out.n_alts = in.n_alts;
+    memcpy(out.len, in.len, sizeof out.len);
+    memcpy(out.allow4, in.allow4, sizeof out.allow4);
+}
+
+int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
+                          int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s) {
+    const int L = q->len;
+    GeneralCtx h;
+    memset(&h, 0, sizeof h);
+    h.L = L; h.M = crit->max_mismatch; h.Gp = crit->max_gap; h.pamless = crit->pamless;
+    h.n_units = crit->n_units; h.n_ops = crit->n_ops; h.n_grna = q->n;
+    h.prune_pattern = crit->max_gap <= 1;
+    for (int i = 0; i < crit->n_units; ++i) {
+        const mg_pattern_unit& u = crit->units[i];
+        h.units[i] = UnitDev{u.n, u.chars, u.start, u.end, u.rvs, u.add_unaligned_m, u.add_unaligned_g,
+                             py_slice_mask(u.start, u.end, L, L)};
+    }
+    {   // validate the postfix program
+        int depth = 0;
+        for (int i = 0; i < crit->n_ops; ++i) {
+            const int op = crit->ops[i];
+            if (op >= 0) { if (op >= crit->n_units) { set_error("pattern op %d references unit %d", i, op); return MG_ERR_ARG; } ++depth; }
+            else { if ((op != MG_OP_AND && op != MG_OP_OR) || depth < 2) { set_error("malformed pattern program at op %d", i); return MG_ERR_ARG; } --depth; }
+            h.ops[i] = op;
+        }
+        if (crit->n_units > 0 && depth != 1) { set_error("malformed pattern program"); return MG_ERR_ARG; }
+    }
+    if (!crit->pamless) {
+        MG_CHECK_ARG(pam->five.n_alts >= 0 && pam->five.n_alts <= MG_MAX_PAM_ALTS && pam->three.n_alts >= 0 && pam->three.n_alts <= MG_MAX_PAM_ALTS);
+        fill_side(pam->five, h.five);
+        fill_side(pam->three, h.three);
+        h.five_max = pam->five_maxlen;
+        h.three_max = pam->three_maxlen;
+    }
+    GeneralCtx* d_ctx = nullptr;
+    MG_CUDA(cudaMalloc(&d_ctx, sizeof h));
+    int rc = MG_OK;
+    cudaError_t e = cudaMemcpyAsync(d_ctx, &h, sizeof h, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);     // h is on this stack frame
+    if (e != cudaSuccess) { cudaFree(d_ctx); set_error("copying criteria: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+
+    // anchors (virtual ends, exclusive) owned by the window range [wb, we): e = p + L
+    const int64_t eb = wb + L, ee = we + L;
+    int K = crit->n_units ? crit->prefilter_edits : crit->max_mismatch + crit->max_gap;
+    if (K >= L) K = -1;
+    // strand -1 anchors: a window [p, p+L) of the forward genome ends, in reverse-complement coordinates, at
+    // glen - p; the shard [wb, we) therefore owns e' in [glen - we + 1, glen - wb + 1)
+    const int64_t mb = g->glen - we + 1, me = g->glen - wb + 1;
+    if (crit->max_gap == 0 && K >= 0) {
+        rc = launch_screen_bitsliced_general(g, q, K, d_ctx, wb, we, d_counts, s);
+    } else {
+        for (int z = 0; z < 2; ++z) {
+            const int strand = z == 0 ? 1 : -1;
+            const int64_t b = z == 0 ? eb : mb, en = z == 0 ? ee : me;
+            const int64_t n_anchor = en - b;
+            if (n_anchor <= 0) continue;
+            if (K < 0) {
+                int64_t grid = (n_anchor * q->n + 127) / 128;
+                if (grid > 148 * 16) grid = 148 * 16;
+                allcells_kernel<<<(unsigned)grid, 128, 0, s>>>(g->view(), q->view(), d_ctx, strand, b, en, d_counts);
+            } else {
+                dim3 grid((unsigned)((n_anchor + kMyersChunk - 1) / kMyersChunk), (unsigned)((q->n + kMyersThreads - 1) / kMyersThreads), 1);
+                myers_kernel<<<grid, kMyersThreads, 0, s>>>(g->view(), q->view(), d_ctx, K, strand, b, en, d_counts);
+            }
+        }
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);     // d_ctx must outlive the kernels
+    cudaFree(d_ctx);
+    if (e != cudaSuccess) { set_error("general screen: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    return rc;
+}
+
 }  // namespace mg

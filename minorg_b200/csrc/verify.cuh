@@ -1,0 +1,275 @@
+// Exact evaluation of the reference's per-hit predicates on the device, over the exhaustive alignment
+// universe E1: for one anchor (gRNA, strand, virtual end e) enumerate every local alignment
+// whose last diagonal ends at e - contiguous query range [qs,qe), first/last column a base pair, at most
+// Gcap gap characters strictly inside - and decide  is_offtarget_pos AND is_offtarget_aln AND
+// is_offtarget_pam  (MINORg.py:2105-2121) for each:
+//   * position : MINORg._is_offtarget_pos (MINORg.py:1994-2000) - span inside ONE masked interval => on-target
+//   * alignment: MINORg._is_offtarget_aln_nopattern (MINORg.py:2018-2044), or the OffTargetExpression
+//                program (ot_regex.py:222-356) over the per-position tuples of BlastHSP (blast.py:46-172,
+//                including the 'dd' grouping of blast.py:114-116)
+//   * PAM      : MINORg._has_pam (MINORg.py:2063-2087), windows clamped to the contig, case-insensitive.
+// Runs only on prefilter survivors (cold path).
+#pragma once
+#include "common.cuh"
+
+namespace mg {
+
+struct UnitDev {
+    int32_t n, chars, start, end, rvs, add_m, add_g;
+    uint32_t mask;   // positions selected by [start:end] on a tuple of exactly L elements (Python slice rules)
+};
+
+struct PamSideDev {
+    int32_t n_alts;
+    int32_t len[MG_MAX_PAM_ALTS];
+    uint8_t allow4[MG_MAX_PAM_ALTS][MG_MAX_PAM_LEN];
+};
+
+struct GeneralCtx {
+    int32_t L, M, Gp, pamless, n_units, n_ops, n_grna;
+    UnitDev units[MG_MAX_PATTERN_UNITS];
+    int32_t ops[MG_MAX_PATTERN_OPS];
+    PamSideDev five, three;
+    int32_t five_max, three_max;
+    int32_t prune_pattern;    // 1: partial pattern evaluation is a sound lower bound (Gp <= 1: no 'dd' elements)
+};
+
+// Python slice [start:end:step] with concrete bounds on a sequence of n elements; step = +1 if end >= start
+// else -1 (blast.py:140-147).  Visits indices first, first+step, ... while (step > 0 ? i < last : i > last).
+__host__ __device__ inline void py_slice_bounds(int start, int end, int n, int& first, int& last, int& step) {
+    step = (end >= start) ? 1 : -1;
+    if (step > 0) {
+        first = start < 0 ? (start + n < 0 ? 0 : start + n) : (start > n ? n : start);
+        last = end < 0 ? (end + n < 0 ? 0 : end + n) : (end > n ? n : end);
+    } else {
+        first = start < 0 ? (start + n < 0 ? -1 : start + n) : (start > n - 1 ? n - 1 : start);
+        last = end < 0 ? (end + n < 0 ? -1 : end + n) : (end > n - 1 ? n - 1 : end);
+    }
+}
+
+__host__ __device__ inline bool py_slice_has(int first, int last, int step, int idx) {
+    return step > 0 ? (idx >= first && idx < last) : (idx <= first && idx > last);
+}
+
+__host__ __device__ inline uint32_t py_slice_mask(int start_or_none, int end_or_none, int qlen, int n) {
+    const int start = start_or_none == MG_SLICE_NONE ? 0 : start_or_none;
+    const int end = end_or_none == MG_SLICE_NONE ? qlen : end_or_none;      // blast.py:138-139: None -> qlen
+    int first, last, step;
+    py_slice_bounds(start, end, n, first, last, step);
+    uint32_t m = 0;
+    for (int i = 0; i < n && i < 32; ++i) if (py_slice_has(first, last, step, i)) m |= 1u << i;
+    return m;
+}
+
+// Strand-aware text: strand +1 = forward genome; -1 = reverse complement, position i' = glen-1-i.
+__device__ __forceinline__ int tbase(const GenomeView& gv, int strand, int64_t i) {
+    if (strand > 0) return base_at(gv, i);
+    const int c = base_at(gv, gv.glen - 1 - i);
+    return c == kCodeInvalid ? c : 3 - c;
+}
+
+struct AlnState {
+    uint32_t mbits;   // mismatch at query position j
+    uint32_t ibits;   // insertion (base only in the gRNA) at query position j
+    uint32_t dA, dB;  // 2-bit count of deletions immediately BEFORE query position j (bit planes)
+    int mm, gaps;
+};
+
+__device__ inline int unit_count(const GeneralCtx& c, const UnitDev& u, const AlnState& a, uint32_t ubits, bool has_dd) {
+    int cnt = 0;
+    if (!u.rvs && has_dd) {
+        // forward tuple with 'dd' elements of their own (blast.py:114-116): walk the elements explicitly
+        int extra = 0;
+        for (int j = 0; j < c.L; ++j) extra += (int)(((a.dA >> j) & 1u) + 2u * ((a.dB >> j) & 1u)) >> 1;
+        const int n = c.L + extra;
+        const int start = u.start == MG_SLICE_NONE ? 0 : u.start;
+        const int end = u.end == MG_SLICE_NONE ? c.L : u.end;
+        int first, last, step;
+        py_slice_bounds(start, end, n, first, last, step);
+        int idx = 0;
+        for (int j = 0; j < c.L; ++j) {
+            const int k = (int)(((a.dA >> j) & 1u) + 2u * ((a.dB >> j) & 1u));
+            for (int r = 0; r < (k >> 1); ++r, ++idx)
+                if (py_slice_has(first, last, step, idx) && (u.chars & MG_CH_DEL)) cnt += 2;
+            if (py_slice_has(first, last, step, idx)) {
+                if ((u.chars & MG_CH_DEL) && (k & 1)) cnt += 1;
+                if ((u.chars & MG_CH_MISMATCH) && ((a.mbits >> j) & 1u)) cnt += 1;
+                if ((u.chars & MG_CH_INS) && ((a.ibits >> j) & 1u)) cnt += 1;
+                if ((ubits >> j) & 1u) cnt += u.add_m + u.add_g;
+            }
+            ++idx;
+        }
+        return cnt;
+    }
+    const uint32_t m = u.mask;
+    if (u.chars & MG_CH_MISMATCH) cnt += __popc(a.mbits & m);
+    if (u.chars & MG_CH_INS) cnt += __popc(a.ibits & m);
+    if (u.chars & MG_CH_DEL) {
+        if (u.rvs) cnt += __popc((a.dA >> 1) & m) + 2 * __popc((a.dB >> 1) & m);   // joined to the previous position
+        else cnt += __popc(a.dA & m) + 2 * __popc(a.dB & m);                       // joined to the next position
+    }
+    cnt += (u.add_m + u.add_g) * __popc(ubits & m);
+    return cnt;
+}
+
+__device__ inline bool pattern_true(const GeneralCtx& c, const AlnState& a, uint32_t ubits) {
+    const bool has_dd = a.dB != 0;
+    unsigned long long stack = 0;   // bit stack
+    int sp = 0;
+    for (int k = 0; k < c.n_ops; ++k) {
+        const int op = c.ops[k];
+        if (op >= 0) {
+            const UnitDev& u = c.units[op];
+            const bool v = unit_count(c, u, a, ubits, has_dd) <= u.n;
+            stack = (stack << 1) | (v ? 1ull : 0ull);
+            ++sp;
+        } else {
+            const unsigned long long b = stack & 1ull, aa = (stack >> 1) & 1ull;
+            stack >>= 2;
+            stack = (stack << 1) | (op == MG_OP_AND ? (aa & b) : (aa | b));
+            --sp;
+        }
+    }
+    return (stack & 1ull) != 0;
+}
+
+__device__ inline bool pam_in_window(const GenomeView& gv, int strand, const PamSideDev& side, int64_t w0, int64_t w1) {
+    // re.search(side, window): some alternative matches somewhere inside [w0, w1)
+    if (side.n_alts == 0) return false;        // MINORg.py:2085-2086: an empty side never matches
+    for (int64_t x = w0; x <= w1; ++x) {
+        for (int a = 0; a < side.n_alts; ++a) {
+            const int len = side.len[a];
+            if (x + len > w1) continue;
+            bool ok = true;
+            for (int k = 0; k < len && ok; ++k) {
+                const int b = tbase(gv, strand, x + k);
+                ok = b < 4 && ((side.allow4[a][k] >> b) & 1);
+            }
+            if (ok) return true;
+        }
+    }
+    return false;
+}
+
+// One complete alignment: query [qs,qe) x subject [s,t) (strand coordinates) inside contig [cs,ce).
+__device__ inline bool alignment_problematic(const GenomeView& gv, const GeneralCtx& c, int strand, const AlnState& a,
+                                             int qs, int qe, int64_t s, int64_t t, int64_t cs, int64_t ce) {
+    const int L = c.L;
+    const int u = L - (qe - qs);
+    if (c.n_units == 0) {
+        const int mq = c.M - a.mm, gq = c.Gp - a.gaps;                       // MINORg.py:2033-2038
+        if (mq < 0 || gq < 0 || mq + gq - u < 0) return false;
+    } else {
+        const uint32_t all = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+        const uint32_t aligned = (qe >= 32 ? 0xFFFFFFFFu : ((1u << qe) - 1u)) & ~((1u << qs) - 1u);
+        if (!pattern_true(c, a, all & ~aligned)) return false;
+    }
+    // position check on the forward-strand span
+    const int64_t fa = strand > 0 ? s : gv.glen - t, fb = strand > 0 ? t : gv.glen - s;
+    if (gv.n_masks && span_masked(gv, fa, fb)) return false;
+    if (c.pamless) return true;
+    const int gap_excess = c.Gp - a.gaps;                                    // MINORg.py:2073-2076
+    const int pre_len = c.five_max + gap_excess + qs;
+    const int post_len = c.three_max + gap_excess + (L - qe);
+    {
+        const int64_t w0 = (s - (pre_len > 0 ? pre_len : 0) < cs) ? cs : s - (pre_len > 0 ? pre_len : 0);
+        if (pam_in_window(gv, strand, c.five, w0, s)) return true;
+    }
+    {
+        const int64_t w1 = (t + (post_len > 0 ? post_len : 0) > ce) ? ce : t + (post_len > 0 ? post_len : 0);
+        if (pam_in_window(gv, strand, c.three, t, w1)) return true;
+    }
+    return false;
+}
+
+// Sound pruning of a PARTIAL alignment (columns known from the 3' end back to query position j):
+// all counters only grow when more columns are added or the 5' end is trimmed.
+__device__ inline bool partial_may_succeed(const GeneralCtx& c, const AlnState& a, int qe) {
+    if (a.gaps > c.Gp) return false;
+    if (c.n_units == 0) {
+        if (a.mm > c.M) return false;
+        return (c.M - a.mm) + (c.Gp - a.gaps) - (c.L - qe) >= 0;
+    }
+    if (!c.prune_pattern) return true;
+    const uint32_t all = c.L >= 32 ? 0xFFFFFFFFu : ((1u << c.L) - 1u);
+    const uint32_t tail = all & ~(qe >= 32 ? 0xFFFFFFFFu : ((1u << qe) - 1u));   // known unaligned 3' positions
+    return pattern_true(c, a, tail);
+}
+
+constexpr int kMaxDepth = MG_MAX_GRNA_LEN + MG_MAX_GAPS + 2;
+
+struct Frame {
+    AlnState a;
+    int j;          // query positions [j, qe) are consumed
+    int64_t t;      // subject positions [t, t_end) are consumed
+    int next;       // next choice to try: 0 pair, 1 insertion, 2 deletion
+    int last_pair;  // the most recent (leftmost) column is a base pair
+};
+
+// gRNA `q` (codes in gRNA orientation, 5'->3'), strand, virtual end e in strand coordinates.
+static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
+                                           int strand, int64_t e) {
+    const int L = c.L;
+    // the contig (strand coordinates) that intersects [e - L - Gp, e)
+    const int64_t lo = e - L - c.Gp, hi = e;
+    const int64_t flo = strand > 0 ? lo : gv.glen - hi, fhi = strand > 0 ? hi : gv.glen - lo;
+    int a0 = 0, a1 = gv.n_contigs - 1, ci = -1;
+    while (a0 <= a1) {
+        const int mid = (a0 + a1) >> 1;
+        if (gv.cstart[mid] < fhi) { ci = mid; a0 = mid + 1; } else a1 = mid - 1;
+    }
+    if (ci < 0 || gv.cend[ci] <= flo) return false;
+    const int64_t cs = strand > 0 ? gv.cstart[ci] : gv.glen - gv.cend[ci];
+    const int64_t ce = strand > 0 ? gv.cend[ci] : gv.glen - gv.cstart[ci];
+
+    Frame st[kMaxDepth];
+    for (int qe = L; qe >= 1; --qe) {
+        const int64_t t_end = e - (L - qe);
+        if (t_end - 1 < cs || t_end > ce) continue;          // the last column must be on the contig
+        int sp = 0;
+        st[0].a = AlnState{0u, 0u, 0u, 0u, 0, 0};
+        st[0].j = qe; st[0].t = t_end; st[0].next = 0; st[0].last_pair = 0;
+        {   // cheap bound on trimming before any work: the 3' trim alone may already break the budget
+            if (!partial_may_succeed(c, st[0].a, qe)) continue;
+        }
+        while (sp >= 0) {
+            Frame& f = st[sp];
+            const int choice = f.next++;
+            if (choice > 2) { --sp; continue; }
+            const bool first_col = (f.j == qe && f.t == t_end);
+            Frame n = f;
+            n.next = 0;
+            if (choice == 0) {
+                if (f.j < 1 || f.t - 1 < cs) continue;
+                const int qb = q[f.j - 1];
+                const int sb = tbase(gv, strand, f.t - 1);
+                const bool same = (qb == sb) && qb < 4;
+                n.j = f.j - 1; n.t = f.t - 1; n.last_pair = 1;
+                if (!same) { n.a.mbits |= 1u << (f.j - 1); n.a.mm++; }
+                if (!partial_may_succeed(c, n.a, qe)) continue;
+                if (alignment_problematic(gv, c, strand, n.a, n.j, qe, n.t, t_end, cs, ce)) return true;
+            } else {
+                if (first_col || f.a.gaps >= c.Gp) continue;
+                if (choice == 1) {           // insertion: consumes query position j-1 only; a pair must follow
+                    if (f.j < 2) continue;
+                    n.j = f.j - 1; n.last_pair = 0;
+                    n.a.ibits |= 1u << (f.j - 1); n.a.gaps++;
+                } else {                     // deletion: consumes subject t-1 only, sits before query position j
+                    if (f.j < 1 || f.t - 2 < cs) continue;
+                    n.t = f.t - 1; n.last_pair = 0;
+                    const uint32_t bit = 1u << f.j;
+                    if (f.j < 32) {
+                        if (n.a.dA & bit) { n.a.dA &= ~bit; n.a.dB ^= bit; if (!(n.a.dB & bit)) { /* 4 deletions: beyond MG_MAX_GAPS */ } }
+                        else n.a.dA |= bit;
+                    }
+                    n.a.gaps++;
+                }
+                if (!partial_may_succeed(c, n.a, qe)) continue;
+            }
+            if (sp + 1 < kMaxDepth) st[++sp] = n;
+        }
+    }
+    return false;
+}
+
+}  // namespace mg

@@ -211,6 +211,51 @@ class OffTargetExpression:
         for i, o in enumerate(ops):
             crit.ops[i] = o
 
+    def edit_bound(self, length, max_gap):
+        """A bound B such that `expression true` implies mismatches + gap characters + unaligned positions
+        <= B for the alignment (hence full-length edit cost <= B): the budget of the device prefilter.
+        Returns -1 when the pattern leaves some position or error type unconstrained (then every cell is
+        handed to the exact verifier).  Sound by construction: a unit 'n m.. <range>' that also counts
+        unaligned positions caps the errors inside its range by n (+ max_gap if it ignores a gap type); the
+        caps of units whose ranges jointly cover every tuple element add up."""
+        def slice_mask(u, n):
+            a = 0 if u.start is None else u.start
+            b = length if u.end is None else u.end          # blast.py:138-139: None -> query length
+            step = 1 if b >= a else -1
+            m = 0
+            for i in list(range(n))[a:b:step]:
+                m |= 1 << i
+            return m
+        worst = 0
+        for clause in self.clauses():
+            usable = [u for u in clause if u.mismatch and self.unaligned_as_mismatch]
+            best = None
+            sizes = [length] + [length + k for k in range(1, max_gap // 2 + 1)]
+            # a cover must hold for every possible tuple length (extra 'dd' elements, blast.py:114-116)
+            cand = usable[:12]
+            for pick in range(1, 1 << len(cand)):
+                chosen = [u for i, u in enumerate(cand) if (pick >> i) & 1]
+                ok = True
+                for n in sizes:
+                    full = (1 << n) - 1
+                    cov = 0
+                    for u in chosen:
+                        cov |= slice_mask(u, n if not u.rvs else length)
+                    if (n == length and cov != full) or (n > length and any(not u.rvs for u in chosen) and cov != full):
+                        ok = False
+                        break
+                if not ok:
+                    continue
+                cost = sum(u.n for u in chosen)
+                if any(not (u.gap or (u.ins and u.dele)) for u in chosen):
+                    cost += max_gap
+                if best is None or cost < best:
+                    best = cost
+            if best is None:
+                return -1
+            worst = max(worst, best)
+        return worst
+
     def clauses(self):
         """Disjunctive normal form: list of clauses, each a list of units (the tree has only AND/OR)."""
         def walk(node):
@@ -224,9 +269,10 @@ class OffTargetExpression:
 
 
 def make_criteria(ot_mismatch=1, ot_gap=0, ot_pattern=None, ot_unaligned_as_mismatch=True,
-                  ot_unaligned_as_gap=False, ot_pamless=True):
+                  ot_unaligned_as_gap=False, ot_pamless=True, grna_length=None):
     """The reference's screen attributes (MINORg.py:686-707) -> `_lib.Criteria`.
-    max_mismatch / max_gap follow MINORg.py:2033-2034."""
+    max_mismatch / max_gap follow MINORg.py:2033-2034.  grna_length lets the host derive the prefilter
+    budget of a pattern (without it every cell goes through the exact verifier)."""
     c = _lib.Criteria()
     c.max_mismatch = max(1, int(ot_mismatch)) - 1
     c.max_gap = max(1, int(ot_gap)) - 1
@@ -238,4 +284,6 @@ def make_criteria(ot_mismatch=1, ot_gap=0, ot_pattern=None, ot_unaligned_as_mism
         expr = ot_pattern if isinstance(ot_pattern, OffTargetExpression) else \
             OffTargetExpression(ot_pattern, ot_unaligned_as_mismatch, ot_unaligned_as_gap)
         expr.lower(c)
+        if grna_length is not None:
+            c.prefilter_edits = expr.edit_bound(int(grna_length), c.max_gap)
     return c

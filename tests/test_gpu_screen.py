@@ -171,3 +171,64 @@ def test_mask_find_vs_oracle(L):
 
 def test_microbench_runs(L):
     assert L.microbench(0) > 1000 and L.microbench(1) > 500
+
+
+def _general_via_abi(L, contigs, masks, grnas, k, glen):
+    from minorg_b200.ot_regex import make_criteria
+    from minorg_b200.pam import PAM
+    blob = np.frombuffer("".join(s for _, s in contigs).encode() or b"\0", dtype=np.uint8)
+    offsets = np.zeros(len(contigs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for _, s in contigs], out=offsets[1:])
+    gb = np.frombuffer("".join(grnas).encode(), dtype=np.uint8)
+    crit = make_criteria(ot_mismatch=k["ot_mismatch"], ot_gap=k["ot_gap"], ot_pattern=k.get("pattern"),
+                         ot_unaligned_as_mismatch=k.get("uam", True), ot_unaligned_as_gap=k.get("uag", False),
+                         ot_pamless=k["pamless"], grna_length=glen)
+    pam = PAM(k["pam"], glen).program()
+    return L.screen_host(blob, offsets, masks, gb, len(grnas), glen, crit, pam)
+
+
+def test_general_golden_cases(L, golden, capsys):
+    """PAM proximity, patterns, gaps: device verdicts vs the verdicts of the reference's own predicates over
+    the exhaustive alignment universe (tests/golden/screen_cases.json)."""
+    bad = []
+    n = 0
+    for c in golden("screen_cases.json")["cases"]:
+        k = c["criteria"]
+        contigs = [tuple(x) for x in c["contigs"]]
+        names = [x[0] for x in contigs]
+        masks = [(names.index(m[1]), m[2], m[3]) for m in c["masks"]]
+        got = _general_via_abi(L, contigs, masks, c["grnas"], k, c["L"])
+        flags = [x > 0 for x in got.tolist()]
+        if flags != c["fail"]:
+            bad.append((c["name"], flags, c["fail"]))
+        n += 1
+    assert not bad, bad
+    assert n >= 30
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_general_random_vs_python_oracle(L, seed):
+    rng = random.Random(100 + seed)
+    glen = rng.choice([10, 12])
+    contigs = [("a", _random_contig(rng, rng.randrange(20, 60), "ACGT" * 5 + "N")), ("b", _random_contig(rng, rng.randrange(3, 30)))]
+    grnas = []
+    for i in range(6):
+        _, seq = contigs[0]
+        p = rng.randrange(0, len(seq) - glen)
+        g = list(seq[p:p + glen].replace("N", "C"))
+        for _ in range(rng.randrange(0, 3)):
+            g[rng.randrange(glen)] = rng.choice("ACGT")
+        if rng.random() < 0.4:
+            del g[rng.randrange(1, glen - 1)]
+            g.append(rng.choice("ACGT"))
+        g = "".join(g)
+        grnas.append(O.reverse_complement(g) if rng.random() < 0.5 else g)
+    k = dict(ot_mismatch=rng.choice([1, 2, 3]), ot_gap=rng.choice([0, 1, 2, 2, 3]),
+             pattern=rng.choice([None, None, "1mg1-", "0mg-5,2mg1-", "1m1-|0g6", "1mi1-,0d-4"]),
+             uam=rng.random() < 0.8, uag=rng.random() < 0.3, pamless=rng.random() < 0.5,
+             pam=rng.choice([".NGG", "TTV.", ".NG", "R{1,2}T"]))
+    masks = [("m", "a", 2, 2 + glen + 3)]
+    crit = O.Criteria(k["ot_mismatch"], k["ot_gap"], k["pattern"], k["uam"], k["uag"], k["pamless"], k["pam"], glen)
+    want, _ = O.screen_exhaustive(grnas, contigs, masks, crit)
+    got = _general_via_abi(L, contigs, [(0, 2, 2 + glen + 3)], grnas, k, glen)
+    assert [x > 0 for x in got.tolist()] == want, (k, grnas, contigs)
