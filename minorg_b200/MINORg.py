@@ -1,0 +1,326 @@
+"""`MINORg` - the slice of the reference's orchestrator class that sits on the hot path, with the same method
+names, arguments, attributes and output files (reference: minorg/MINORg.py, class MINORg):
+
+    grna()                      MINORg.py:1917-1927   PAM enumeration over self.target  -> self.grna_hits
+    filter_background(...)      MINORg.py:2146-2220   mask on-targets, screen every genome, set 'background'
+    _mask_ontargets(*fnames)    MINORg.py:1933-1967   -> self.masked {filename: tuple(Masked)}
+    _offtarget_hits(subject)    MINORg.py:2123-2144   -> set of failing gRNA ids
+    write_mask_report(fout)     MINORg.py:1969-1992
+
+Everything the reference delegates to `regex` and to `blastn` subprocesses runs on the GPU through
+libminorg_b200.so; there is no CPU fallback.  Target discovery (`seq()`), feature/GC filters and the
+minimum-set step are outside this path: `target` must be given as a FASTA file."""
+import os
+
+import numpy as np
+
+from . import _lib
+from .fasta import fasta_to_dict, read_fasta, reverse_complement
+from .generate_grna import find_multi_gRNA
+from .ot_regex import MINORgError, OffTargetExpression, make_criteria
+from .pam import PAM
+
+
+class Masked:
+    """A masked (on-target) interval: 0-based, end-exclusive (filter_grna.py:44-65)."""
+
+    def __init__(self, masked, molecule, start, end):
+        self.masked, self.molecule, self.start, self.end = masked, molecule, int(start), int(end)
+
+    def __eq__(self, other):
+        return isinstance(other, Masked) and (self.masked, self.molecule, self.start, self.end) == \
+            (other.masked, other.molecule, other.start, other.end)
+
+    def __hash__(self):
+        return hash((self.masked, self.molecule, self.start, self.end))
+
+    def __repr__(self):
+        return "Masked(%s, %s, %d, %d)" % (self.masked, self.molecule, self.start, self.end)
+
+    def within(self, r):
+        a, b = int(min(r)), int(max(r))
+        return a >= self.start and b <= self.end
+
+
+def _fname(x):
+    return getattr(x, "filename", None) or getattr(x, "fasta", None) or str(x)
+
+
+def _find_identical_host(seqs, records):
+    """Mask sequences with non-ACGT characters: case-sensitive exact string search of the sequence and its
+    reverse complement, where 'N' matches only 'N' - the reference does this on the host too
+    (fasta.find_identical_in_fasta, fasta.py:45-95); it is string matching, not part of the device path."""
+    out = []
+    for sid, seq in seqs:
+        for needle in {seq, reverse_complement(seq)}:
+            for cid, text in records:
+                pos = text.find(needle)
+                while pos >= 0:
+                    out.append(Masked(sid, cid, pos, pos + len(needle)))
+                    pos = text.find(needle, pos + 1)
+    return out
+
+
+class MINORg:
+    def __init__(self, directory=None, prefix="minorg", thread=1, keep_tmp=False, device=None, **kwargs):
+        self.directory = os.path.abspath(directory or os.getcwd())
+        self.prefix = prefix
+        self.thread = thread                  # kept for API parity; the GPU path does not fork workers
+        self.keep_tmp = keep_tmp
+        self.auto_update_files = True
+        # hot-path attributes and their reference defaults (parse_config.py:460-513, MINORg.py:686-707)
+        self.target = None
+        self.mask = []
+        self.query = {}
+        self.background = {}
+        self.reference = {}
+        self.genes = None
+        self.ref_gene = None
+        self.screen_reference = True
+        self.query_reference = False
+        self.ot_mismatch = 1
+        self.ot_gap = 0
+        self.ot_pamless = True
+        self._ot_unaligned_as_mismatch = True
+        self._ot_unaligned_as_gap = False
+        self._ot_pattern = None
+        self._pam = None
+        self._length = 20
+        self.pam = ".NGG"
+        self.accept_invalid = False
+        self.grna_hits = None
+        self.grna_fasta = None
+        self.grna_map = None
+        self.pass_fasta = None
+        self.pass_map = None
+        self.masked = {}
+        self._genomes = {}
+        dev = int(os.environ.get("MINORG_B200_DEVICE", "0")) if device is None else int(device)
+        self.device_name, self.device_sms = _lib.init(dev)
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    # ---- attributes with the reference's setter behaviour (MINORg.py:969-1012) -----------------
+    @property
+    def pam(self):
+        return self._pam
+
+    @pam.setter
+    def pam(self, pam):
+        self._pam = PAM(pam=pam, gRNA_length=self._length)
+
+    @property
+    def length(self):
+        return self._length
+
+    @length.setter
+    def length(self, length):
+        self._length = length
+        self._pam = PAM(pam=self._pam.raw_pam if self._pam is not None else ".NGG", gRNA_length=length)
+
+    @property
+    def ot_pattern(self):
+        return self._ot_pattern
+
+    @ot_pattern.setter
+    def ot_pattern(self, pattern):
+        if pattern is None or isinstance(pattern, OffTargetExpression):
+            self._ot_pattern = pattern
+        else:
+            self._ot_pattern = OffTargetExpression(pattern, unaligned_as_mismatch=self._ot_unaligned_as_mismatch,
+                                                   unaligned_as_gap=self._ot_unaligned_as_gap)
+
+    @property
+    def ot_unaligned_as_mismatch(self):
+        return self._ot_unaligned_as_mismatch
+
+    @ot_unaligned_as_mismatch.setter
+    def ot_unaligned_as_mismatch(self, v):
+        self._ot_unaligned_as_mismatch = bool(v)
+        if self._ot_pattern is not None:      # (the reference raises AttributeError here: typo at MINORg.py:1003)
+            self.ot_pattern = self._ot_pattern.pattern
+
+    @property
+    def ot_unaligned_as_gap(self):
+        return self._ot_unaligned_as_gap
+
+    @ot_unaligned_as_gap.setter
+    def ot_unaligned_as_gap(self, v):
+        self._ot_unaligned_as_gap = bool(v)
+        if self._ot_pattern is not None:
+            self.ot_pattern = self._ot_pattern.pattern
+
+    # ---- files ---------------------------------------------------------------------------------
+    def results_fname(self, name):
+        d = os.path.join(self.directory, self.prefix)
+        os.makedirs(d, exist_ok=True)
+        return os.path.join(d, "%s_%s" % (self.prefix, name))
+
+    def add_query(self, fname, alias=None):
+        self.query[alias or "query_%d" % (len(self.query) + 1)] = str(fname)
+
+    def add_background(self, fname, alias=None):
+        self.background[alias or "bg_%d" % (len(self.background) + 1)] = str(fname)
+
+    def write_all_grna_fasta(self, fout=None):
+        fout = fout or self.grna_fasta or self.results_fname("gRNA_all.fasta")
+        self.grna_fasta = fout
+        self.grna_hits.write_fasta(fout, write_all=True)
+
+    def write_all_grna_map(self, fout=None, write_checks=True):
+        fout = fout or self.grna_map or self.results_fname("gRNA_all.map")
+        self.grna_map = fout
+        self.grna_hits.write_mapping(fout, write_all=True, write_checks=write_checks)
+
+    def valid_grna(self):
+        """Sequences whose set sequence-level checks all pass (MINORg.py:1177-1233, sequence checks only)."""
+        names = [n for n in ("background", "GC") if any(s.check(n) is not None for s in self.grna_hits.flatten_gRNAseqs())]
+        return self.grna_hits.filter_seqs(*names, accept_invalid=self.accept_invalid) if names else self.grna_hits.seqs
+
+    def write_pass_grna_files(self, fasta=None, map=None):
+        seqs = self.valid_grna()
+        self.pass_map = map or self.pass_map or self.results_fname("gRNA_pass.map")
+        self.pass_fasta = fasta or self.pass_fasta or self.results_fname("gRNA_pass.fasta")
+        if seqs:
+            self.grna_hits.write_mapping(self.pass_map, sets=[seqs], write_checks=False)
+            self.grna_hits.write_fasta(self.pass_fasta, seqs=seqs)
+        else:
+            open(self.pass_map, "w").close()
+            open(self.pass_fasta, "w").close()
+
+    # ---- sub-command: gRNA ---------------------------------------------------------------------
+    def _generate_grna(self, fname, pam=None, length=None):
+        return find_multi_gRNA(fname, pam=self.pam if pam is None else pam,
+                               gRNA_len=self.length if length is None else length)
+
+    def grna(self):
+        """Generate all possible gRNA from self.target based on self.pam and self.length."""
+        if not self.target:
+            raise MINORgError("MINORg.grna requires self.target (FASTA of target sequences)")
+        self.grna_hits = self._generate_grna(self.target, pam=self.pam, length=self.length)
+        self.write_all_grna_fasta()
+        if self.auto_update_files:
+            self.write_all_grna_map()
+
+    # ---- sub-command: filter (background) ------------------------------------------------------
+    def _genome(self, fname):
+        """Packed genome of a FASTA file, resident in HBM (cached per file)."""
+        fname = _fname(fname)
+        if fname not in self._genomes:
+            records = read_fasta(fname)
+            self._genomes[fname] = (_lib.Genome.from_contigs(records), [r[0] for r in records], records)
+        return self._genomes[fname]
+
+    def _subject_groups(self):
+        ref = {a: _fname(r) for a, r in self.reference.items()}
+        return ref, {a: _fname(f) for a, f in self.query.items()}, {a: _fname(f) for a, f in self.background.items()}
+
+    def _mask_ontargets(self, *mask_fnames):
+        """All intervals of every subject file identical (end to end, either strand) to a sequence of the
+        given FASTA files."""
+        self.masked = {}
+        seqs = []
+        for mf in mask_fnames:
+            if mf:
+                seqs.extend(fasta_to_dict(mf).items())
+        plain = [(i, s) for i, s in seqs if s and set(s) <= set("ACGTacgt")]
+        other = [(i, s) for i, s in seqs if s and not set(s) <= set("ACGTacgt")]
+        for group in self._subject_groups():
+            for fname in group.values():
+                if fname in self.masked:
+                    continue
+                genome, names, records = self._genome(fname)
+                found = set()
+                if plain:
+                    for si, ci, start, end, _strand in genome.find_exact([s for _, s in plain]):
+                        found.add(Masked(plain[si][0], names[ci], start, end))
+                if other:
+                    found.update(_find_identical_host(other, records))
+                self.masked[fname] = tuple(found)
+
+    def write_mask_report(self, fout):
+        ref, query, bg = self._subject_groups()
+        inv = {}
+        for alias, fname in list(ref.items()) + list(query.items()) + list(bg.items()):
+            inv[fname] = alias                                   # later aliases win, like the dict merge at :1980-1983
+        with open(fout, "w") as f:
+            f.write("#alias\tfname\n")
+            for fname, alias in inv.items():
+                f.write("#%s\t%s\n" % (alias, fname))
+            f.write("\t".join(["source", "molecule", "start", "end", "masked"]) + "\n")
+            for fname, masked in self.masked.items():
+                for m in masked:
+                    f.write("\t".join([str(inv[fname]), m.molecule, str(m.start), str(m.end), m.masked]) + "\n")
+
+    def _criteria(self, length):
+        return make_criteria(ot_mismatch=self.ot_mismatch, ot_gap=self.ot_gap, ot_pattern=self.ot_pattern,
+                             ot_unaligned_as_mismatch=self.ot_unaligned_as_mismatch,
+                             ot_unaligned_as_gap=self.ot_unaligned_as_gap, ot_pamless=self.ot_pamless,
+                             grna_length=length)
+
+    def offtarget_counts(self, fasta_subject, seqs):
+        """Per-sequence count of problematic, unmasked alignments in one subject file (device screen)."""
+        import torch
+        fname = _fname(fasta_subject)
+        genome, names, _ = self._genome(fname)
+        index = {n: i for i, n in enumerate(names)}
+        genome.set_masks([(index[m.molecule], m.start, m.end) for m in self.masked.get(fname, ()) if m.molecule in index])
+        out = np.zeros(len(seqs), dtype=np.int64)
+        by_len = {}
+        for i, s in enumerate(seqs):
+            by_len.setdefault(len(s), []).append(i)
+        stream = torch.cuda.current_stream().cuda_stream
+        for length, idx in by_len.items():
+            q = _lib.Queries([seqs[i] for i in idx], stream=stream)
+            counts = torch.zeros(2 * len(idx), dtype=torch.int32, device="cuda")
+            pam = PAM(self.pam, length).program() if not self.ot_pamless else None
+            _lib.screen(genome, q, self._criteria(length), pam, counts.data_ptr(), stream=stream)
+            c = counts.cpu().numpy().astype(np.int64)
+            out[idx] = c[:len(idx)] + c[len(idx):]
+            q.free()
+        return out
+
+    def _offtarget_hits(self, fasta_subject, keep_output=False, fout=None, thread=None):
+        """ids of the gRNA of self.grna_fasta with a problematic off-target hit in `fasta_subject`."""
+        if self.grna_fasta is None:
+            self.write_all_grna_fasta()
+        ids_seqs = list(fasta_to_dict(self.grna_fasta).items())
+        if not ids_seqs:
+            return set()
+        counts = self.offtarget_counts(fasta_subject, [s for _, s in ids_seqs])
+        return {ids_seqs[i][0] for i in np.nonzero(counts)[0].tolist()}
+
+    def filter_background(self, *other_mask_fnames, keep_blast_output=None, mask_reference=True):
+        """Set the 'background' check of every candidate gRNA: mask on-targets in all subject files, screen
+        all gRNA against reference (if screen_reference or query_reference), query and background files."""
+        if not self.grna_hits:
+            raise MINORgError("MINORg.filter_background requires gRNA (generated with self.grna())")
+        if self.grna_fasta is None:
+            self.write_all_grna_fasta()
+        print("Masking on-targets")
+        self._mask_ontargets(self.target, *([self.ref_gene] if (mask_reference and self.genes and self.ref_gene) else []),
+                             *self.mask, *other_mask_fnames)
+        self.write_mask_report(self.results_fname("masked.txt"))
+        print("Finding off-targets")
+        ref, query, bg = self._subject_groups()
+        excl, screened = set(), set()
+        for enabled, group in (((self.screen_reference or self.query_reference) and ref, ref), (query, query), (bg, bg)):
+            if not enabled:
+                continue
+            for fname in group.values():
+                if fname not in screened:
+                    excl |= self._offtarget_hits(fname)
+            screened |= set(group.values())
+        grna_seqs = fasta_to_dict(self.grna_fasta)
+        failed = {str(grna_seqs[i]).upper() for i in excl}
+        passed = {str(s).upper() for s in grna_seqs.values()} - failed
+        self.grna_hits.set_seqs_check("background", True, passed)
+        self.grna_hits.set_seqs_check("background", False, failed)
+        if self.auto_update_files:
+            self.write_all_grna_map()
+            self.write_pass_grna_files()
+
+    def close(self):
+        for g, _, _ in self._genomes.values():
+            g.free()
+        self._genomes = {}

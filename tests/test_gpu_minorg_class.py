@@ -1,0 +1,111 @@
+"""The MINORg-shaped class end to end on BASELINE.json configs[0] (the reference's bundled Arabidopsis subset):
+grna() + filter_background() on the GPU vs the CPU oracle applying the reference's criteria."""
+import gzip
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, minorg_oracle as O
+
+pytestmark = pytest.mark.gpu
+CFG1 = os.path.join(os.path.dirname(__file__), "golden", "config1")
+
+
+@pytest.fixture(scope="module")
+def cfg1(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cfg1")
+    for f in ("subset_ref_TAIR10.fasta", "subset_9654.fasta", "subset_9655.fasta"):
+        with gzip.open(os.path.join(CFG1, f + ".gz"), "rb") as i, open(d / f, "wb") as o:
+            shutil.copyfileobj(i, o)
+    shutil.copy(os.path.join(CFG1, "targets.fasta"), d / "targets.fasta")
+    return d
+
+
+def _oracle_background(d, grna_entries, subjects, ot_mismatch):
+    targets = O.read_fasta(str(d / "targets.fasta"))
+    seqs = [s for s, _ in grna_entries]
+    fail = np.zeros(len(seqs), dtype=bool)
+    all_masks = {}
+    for f in subjects:
+        contigs = O.read_fasta(str(d / f))
+        names = [c[0] for c in contigs]
+        masks = O.find_masks(targets, contigs)
+        all_masks[f] = masks
+        counts = c_oracle.screen_hamming(contigs, [(names.index(c), s, e) for _, c, s, e in masks], seqs,
+                                         max(1, ot_mismatch) - 1, threads=8)
+        fail |= counts > 0
+    return fail, all_masks
+
+
+@pytest.mark.parametrize("ot_mismatch", [1, 2, 3])
+def test_config1_grna_and_filter_background(cfg1, tmp_path, ot_mismatch, capsys):
+    from minorg_b200.MINORg import MINORg
+    m = MINORg(directory=str(tmp_path), prefix="cfg1")
+    m.target = str(cfg1 / "targets.fasta")
+    m.reference = {"TAIR10": str(cfg1 / "subset_ref_TAIR10.fasta")}
+    m.add_query(str(cfg1 / "subset_9654.fasta"), alias="9654")
+    m.add_query(str(cfg1 / "subset_9655.fasta"), alias="9655")
+    m.ot_mismatch = ot_mismatch
+    m.grna()
+    want = O.find_multi_grna(m.target, ".NGG", 20)
+    assert m.grna_hits.seqs == [s for s, _ in want] and len(want) == 733
+    assert open(m.grna_fasta).read() == O.grna_fasta_text(want)
+    assert open(m.grna_map).read() == O.grna_map_text(want)
+    m.filter_background()
+    assert "Masking on-targets" in capsys.readouterr().out
+    subjects = ["subset_ref_TAIR10.fasta", "subset_9654.fasta", "subset_9655.fasta"]
+    fail, masks = _oracle_background(cfg1, want, subjects, ot_mismatch)
+    got_fail = np.array([m.grna_hits.get_gRNAseq_by_seq(s).check("background") is False for s, _ in want])
+    assert np.array_equal(got_fail, fail)
+    assert 0 < fail.sum() < len(fail)                        # both outcomes occur
+    for f in subjects:
+        got = {(x.masked, x.molecule, x.start, x.end) for x in m.masked[str(cfg1 / f)]}
+        assert got == masks[f]
+    assert ("AT5G45050", "chromA", 13, 4905) in masks["subset_ref_TAIR10.fasta"]
+    # files: .map carries the background column, pass files hold exactly the passing gRNA, mask report format
+    status = {(s, "background"): ("fail" if fl else "pass") for (s, _), fl in zip(want, fail)}
+    assert open(m.grna_map).read() == O.grna_map_text(want, status=status)
+    passed = [l for l in open(m.pass_fasta).read().splitlines() if not l.startswith(">")]
+    assert passed == [s for (s, _), fl in zip(want, fail) if not fl]
+    rep = open(os.path.join(str(tmp_path), "cfg1", "cfg1_masked.txt")).read().splitlines()
+    assert rep[0] == "#alias\tfname" and "source\tmolecule\tstart\tend\tmasked" in rep
+    assert any(l.split("\t")[:4] == ["TAIR10", "chromA", "13", "4905"] for l in rep)
+    m.close()
+
+
+def test_config1_pattern_and_pam_modes(cfg1, tmp_path):
+    """Same data through the general screen: --ot-pattern, gaps, PAM proximity (flags vs the Python oracle on a
+    small slice so the exhaustive enumeration stays cheap)."""
+    from minorg_b200.MINORg import MINORg
+    ref = O.read_fasta(str(cfg1 / "subset_ref_TAIR10.fasta"))
+    small = tmp_path / "small.fasta"
+    with open(small, "w") as f:
+        f.write(">chromA\n%s\n>chromB\n%s\n" % (ref[0][1][4800:5150], ref[1][1][:90]))
+    tgt = tmp_path / "t.fasta"
+    with open(tgt, "w") as f:
+        f.write(">t1\n%s\n" % ref[0][1][4850:4990])
+    for kw in (dict(ot_mismatch=2, ot_gap=2), dict(ot_mismatch=2, ot_pamless=False), dict(ot_pattern="0mg-8,2mg1-", ot_gap=2),
+               dict(ot_mismatch=1, ot_gap=2, ot_pamless=False, pam="TTV.")):
+        m = MINORg(directory=str(tmp_path), prefix="p")
+        m.length = 14
+        for k, v in kw.items():
+            setattr(m, k, v)
+        m.target = str(tgt)
+        m.add_background(str(small), alias="bg")
+        m.screen_reference = False
+        m.grna()
+        seqs = m.grna_hits.seqs[:6]
+        m.grna_hits._gRNAseqs = {s: m.grna_hits._gRNAseqs[s] for s in seqs}
+        m.grna_hits._hits = {s: m.grna_hits._hits[s] for s in seqs}
+        m.write_all_grna_fasta()
+        m.filter_background()
+        contigs = O.read_fasta(str(small))
+        masks = O.find_masks(O.read_fasta(str(tgt)), contigs)
+        crit = O.Criteria(kw.get("ot_mismatch", 1), kw.get("ot_gap", 0), kw.get("ot_pattern"), True, False,
+                          kw.get("ot_pamless", True), kw.get("pam", ".NGG"), 14)
+        want, _ = O.screen_exhaustive(seqs, contigs, masks, crit)
+        got = [m.grna_hits.get_gRNAseq_by_seq(s).check("background") is False for s in seqs]
+        assert got == want, kw
+        m.close()
