@@ -1,4 +1,6 @@
 // C-ABI glue: screen dispatch, host-buffer convenience path, integer-pipe microbenchmarks.
+#include <ctime>
+
 #include "common.cuh"
 
 using namespace mg;
@@ -108,9 +110,14 @@ int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
     mg_genome* g = nullptr;
     mg_queries* q = nullptr;
     uint32_t* d_counts = nullptr;
+    const bool trace = getenv("MG_TRACE") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t0 = now();
     int rc = mg_genome_from_ascii(seq, offsets, n_contigs, stream, &g);
+    const double t1 = now();
     if (rc == MG_OK) rc = mg_genome_set_masks(g, mask_contig, mask_start, mask_end, n_masks, stream);
     if (rc == MG_OK) rc = mg_queries_create(grna, n, len, stream, &q);
+    const double t2 = now();
     if (rc == MG_OK && n > 0) {
         if (cudaMalloc(&d_counts, sizeof(uint32_t) * 2 * (size_t)n) != cudaSuccess) { set_error("cudaMalloc(counts) failed"); rc = MG_ERR_NOMEM; }
     }
@@ -125,9 +132,12 @@ int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
         if (e != cudaSuccess) { set_error("screen failed: %s", cudaGetErrorString(e)); rc = MG_ERR_CUDA; }
         else for (int i = 0; i < n; ++i) counts_out[i] = tmp[i] + tmp[(size_t)n + i];
     }
+    const double t3 = now();
     cudaFree(d_counts);
     mg_queries_free(q);
     mg_genome_free(g);
+    if (trace) fprintf(stderr, "[mg_screen_host] genome H2D+pack %.1f ms, masks+queries %.1f ms, screen+D2H %.1f ms, free %.1f ms\n",
+                       t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
 

@@ -13,6 +13,10 @@
 namespace mg {
 
 void set_error(const char* fmt, ...);
+// Stream-ordered allocations from the device's default memory pool (kept warm: cudaFree of a 0.4 GB plane
+// costs hundreds of ms, a pool free costs microseconds - matters for the host-buffer end-to-end call).
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t s);
+void dev_free(void* p, cudaStream_t s);
 
 #define MG_CUDA(call)                                                                        \
     do {                                                                                     \

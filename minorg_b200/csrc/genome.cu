@@ -18,6 +18,26 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err.c_str(); }
 
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t s) {
+    static thread_local int configured_for = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_for != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;      // never trim: later calls reuse the planes
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured_for = dev;
+    }
+    return cudaMallocAsync(p, bytes, s);
+}
+
+void dev_free(void* p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
 // One thread packs 32 consecutive bases of one contig: two 2-bit words + one invalid word.
 // HBM-bound: reads 1 B/base (two 16-B vector loads per thread), writes 0.375 B/base.
 __global__ void __launch_bounds__(256)
@@ -78,7 +98,7 @@ int launch_pack(const char* d_ascii, const std::vector<int64_t>& offsets, mg_gen
     return MG_OK;
 }
 
-static int genome_alloc(const int64_t* offsets, int n_contigs, mg_genome** out) {
+static int genome_alloc(const int64_t* offsets, int n_contigs, cudaStream_t s, mg_genome** out) {
     MG_CHECK_ARG(offsets != nullptr && n_contigs >= 0 && out != nullptr);
     mg_genome* g = new mg_genome();
     MG_CUDA(cudaGetDevice(&g->device));
@@ -97,8 +117,8 @@ static int genome_alloc(const int64_t* offsets, int n_contigs, mg_genome** out) 
     g->glen = (pos + 127) / 128 * 128;
     g->bases_words = (size_t)(g->glen / 16) + 8;
     g->invalid_words = (size_t)(g->glen / 32) + 8;
-    MG_CUDA(cudaMalloc(&g->d_bases, g->bases_words * 4));
-    MG_CUDA(cudaMalloc(&g->d_invalid, g->invalid_words * 4));
+    MG_CUDA(dev_alloc((void**)&g->d_bases, g->bases_words * 4, s));
+    MG_CUDA(dev_alloc((void**)&g->d_invalid, g->invalid_words * 4, s));
     const size_t nb = sizeof(int64_t) * (size_t)std::max(1, n_contigs);
     MG_CUDA(cudaMalloc(&g->d_cstart, nb));
     MG_CUDA(cudaMalloc(&g->d_cend, nb));
@@ -140,7 +160,7 @@ int mg_init(int device, char* name_out, int name_cap, int* sm_count_out) {
 
 int mg_genome_from_device_ascii(const char* d_seq, const int64_t* offsets, int n_contigs, void* stream, mg_genome** out) {
     mg_genome* g = nullptr;
-    int rc = genome_alloc(offsets, n_contigs, &g);
+    int rc = genome_alloc(offsets, n_contigs, (cudaStream_t)stream, &g);
     if (rc) return rc;
     std::vector<int64_t> off(offsets, offsets + n_contigs + 1);
     rc = launch_pack(d_seq, off, g, (cudaStream_t)stream);
@@ -155,16 +175,16 @@ int mg_genome_from_ascii(const char* seq, const int64_t* offsets, int n_contigs,
     MG_CHECK_ARG(total == 0 || seq != nullptr);
     cudaStream_t s = (cudaStream_t)stream;
     char* d_seq = nullptr;
-    MG_CUDA(cudaMalloc(&d_seq, (size_t)std::max<int64_t>(total, 16) + 32));
+    MG_CUDA(dev_alloc((void**)&d_seq, (size_t)std::max<int64_t>(total, 16) + 32, s));
     std::vector<int64_t> rel(n_contigs + 1);
     for (int i = 0; i <= n_contigs; ++i) rel[i] = offsets[i] - offsets[0];
     if (total) {
         cudaError_t e = cudaMemcpyAsync(d_seq, seq + offsets[0], (size_t)total, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { cudaFree(d_seq); set_error("H2D copy of genome failed: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+        if (e != cudaSuccess) { dev_free(d_seq, s); set_error("H2D copy of genome failed: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     }
     int rc = mg_genome_from_device_ascii(d_seq, rel.data(), n_contigs, stream, out);
-    cudaStreamSynchronize(s);
-    cudaFree(d_seq);
+    dev_free(d_seq, s);      // stream-ordered: released once the pack kernels are done
+    cudaStreamSynchronize(s);   // the caller may reuse `seq` as soon as we return
     return rc;
 }
 
@@ -215,7 +235,7 @@ int mg_genome_set_masks(mg_genome* g, const int32_t* contig, const int64_t* star
 
 void mg_genome_free(mg_genome* g) {
     if (!g) return;
-    cudaFree(g->d_bases); cudaFree(g->d_invalid); cudaFree(g->d_cstart); cudaFree(g->d_cend);
+    dev_free(g->d_bases, 0); dev_free(g->d_invalid, 0); cudaFree(g->d_cstart); cudaFree(g->d_cend);
     cudaFree(g->d_mstart); cudaFree(g->d_mend_pm);
     delete g;
 }

@@ -80,12 +80,14 @@ __device__ __noinline__ void verify_hits(const GenomeView& gv, const QueriesView
     }
 }
 
-template <int L, int K, int THREADS, bool GENERAL>
+template <int L, int K, int THREADS, bool GENERAL, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chunk, int64_t wb, int64_t we,
                         uint32_t* __restrict__ counts, const GeneralCtx* __restrict__ gctx) {
     constexpr int S = 4 * L + 1;                     // table words per group
     constexpr int NB = mgcsa::CountBits<L>::value;
+    constexpr int T1 = SPLIT ? mgcsa::SplitOf<L>::value : 0;      // positions summed before the early-out test
+    constexpr int NB1 = mgcsa::CountBits<(T1 > 0 ? T1 : 1)>::value;
     extern __shared__ uint32_t tab[];
 
     // contiguous, warp-aligned window range of this CTA
@@ -120,12 +122,34 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
             const char* t = reinterpret_cast<const char*>(tab);
 #pragma unroll 1
             for (int g = 0; g < ng; ++g, t += S * 4) {
-                uint32_t x[L];
+                uint32_t hit;
+                if constexpr (T1 > 0) {
+                    // Stage 1: the first T1 positions.  The count can only grow, so a query already over budget
+                    // is decided; on random sequence a whole warp (32 windows x 32 queries) is over budget ~90 %
+                    // of the time at L=20, K=4, and the remaining L-T1 loads and their adders are skipped.
+                    // Every cell is still decided exactly - no verdict is skipped, only arithmetic whose result
+                    // cannot change it.
+                    uint32_t x1[T1];
 #pragma unroll
-                for (int j = 0; j < L; ++j) x[j] = *reinterpret_cast<const uint32_t*>(t + off[j]);
-                uint32_t bits[NB];
-                mgcsa::csa_count<L>(x, bits);
-                const uint32_t hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
+                    for (int j = 0; j < T1; ++j) x1[j] = *reinterpret_cast<const uint32_t*>(t + off[j]);
+                    uint32_t part[NB1];
+                    mgcsa::csa_count<T1>(x1, part);
+                    const uint32_t alive = (K >= 0) ? le_const_impl<NB1>(part, K) : le_runtime<NB1>(part, kthr);
+                    if (!__any_sync(0xFFFFFFFFu, alive != 0u)) continue;
+                    uint32_t x2[L - T1];
+#pragma unroll
+                    for (int j = T1; j < L; ++j) x2[j - T1] = *reinterpret_cast<const uint32_t*>(t + off[j]);
+                    uint32_t bits[NB];
+                    mgcsa::csa_count_rest<L>(part, x2, bits);
+                    hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
+                } else {
+                    uint32_t x[L];
+#pragma unroll
+                    for (int j = 0; j < L; ++j) x[j] = *reinterpret_cast<const uint32_t*>(t + off[j]);
+                    uint32_t bits[NB];
+                    mgcsa::csa_count<L>(x, bits);
+                    hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
+                }
                 if (hit) {
                     if (GENERAL) verify_hits(gv, qv, gctx, hit, cg + g, p, counts);
                     else report_hits(gv, 2 * qv.n, L, hit, cg + g, p, counts);
@@ -147,7 +171,7 @@ static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t
     const int max_groups = (smem_max - 1024) / (S * 4);
     const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
     const size_t smem = (size_t)gpc * S * 4;
-    auto kern = screen_bitsliced_kernel<L, K, THREADS, GENERAL>;
+    auto kern = screen_bitsliced_kernel<L, K, THREADS, GENERAL, true>;
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nwin = we - wb;
     int64_t grid = (nwin + THREADS - 1) / THREADS;
