@@ -29,6 +29,9 @@ TARGETS_PER_GENOME = 64
 TARGET_LEN = 2000
 GRNA_LEN = 20
 MAX_MISMATCH = 4
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-size (8x135 Mb, N=1) scan launch, from the ncu capture
+# summarised in profiles/ (see DESIGN.md); algorithmic bytes are 405 MB genome + 30 MB of query tables (148 CTAs x 202.5 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 445207296   # profiles/r01_bitsliced_v2_fullsize_ncu_full.tsv: 430.43 MB read + 14.78 MB written
 
 
 def parse_args():
@@ -305,6 +308,7 @@ def main():
     # sanity on the result itself (full-size property): every gRNA cut from a planted target hits random
     # sequence ~835 times per 1.08 Gbp at <=4 mismatches; on-target copies are masked.
     n = len(grnas)
+    steps_cnt, stage2 = _lib.last_screen_stats()
     host_counts = (counts[:n] + counts[n:]).cpu().numpy()
     fails = int((host_counts > 0).sum())
 
@@ -353,21 +357,34 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel (screen_bitsliced_kernel)
+    # The scan is bound by the shared-memory load pipe (LSU, one 32-bit load per lane per gRNA position per 32
+    # queries) and by the ALU pipe (LOP3 adders) at nearly the same level; HBM carries 0.375 B/base once per
+    # launch and is ~4 orders of magnitude below its roofline.  Denominators: mg_microbench measures both
+    # pipes on this GPU; the work per (warp, 32-query group) step is counted by the kernel itself
+    # (mg_last_screen_stats): every step loads/sums the first T1 positions, a fraction f2 the remaining L-T1.
     peaks, peaks_src = measured_peaks()
     lop3 = _lib.microbench(0, stream)     # Glane-ops/s, measured here
     lds = _lib.microbench(1, stream)
     my_bases = sum(clens) * len(my_genomes)
     cells_per_launch = 2.0 * n * my_bases
     achieved = cells_per_launch / (kern_ms / 1e3) / 1e12
-    alu_ops_per_32cells = 39.0          # LOP3 per (window, 32 queries) at L=20: 36 adder + 3 compare (SASS)
-    peak_lsu = lds * 1e9 * 32.0 / GRNA_LEN / 1e12
-    peak_alu = lop3 * 1e9 * 32.0 / alu_ops_per_32cells / 1e12
+    t1 = (3 * GRNA_LEN + 3) // 4
+    f2 = (stage2 / steps_cnt) if steps_cnt else 1.0
+    loads_per_step = t1 + f2 * (GRNA_LEN - t1)
+    alu_per_step = 25.0 + f2 * 17.0        # SASS: 22 adder + 2 compare LOP3 + 1 ISETP, then 14 adder + 3 compare
+    peak_lsu = lds * 1e9 * 32.0 / loads_per_step / 1e12
+    peak_alu = lop3 * 1e9 * 32.0 / alu_per_step / 1e12
     peak = min(peak_lsu, peak_alu)
-    alg_bytes = my_bases * 0.375 + queries.n * 2 * 0  # packed genome streamed once per launch
-    roofline = {"bound": "lsu(shared)" if peak_lsu <= peak_alu else "alu", "achieved": achieved, "peak": peak,
-                "unit": "Tcell/s", "frac": achieved / peak, "traffic": None,
+    brute = lds * 1e9 * 32.0 / GRNA_LEN / 1e12
+    alg_bytes = my_bases * 0.375          # packed genome (2-bit bases + 1-bit invalid plane) streamed once per launch
+    roofline = {"bound": "lsu(shared-memory loads)" if peak_lsu <= peak_alu else "alu(lop3)", "achieved": achieved,
+                "peak": peak, "unit": "Tcell/s", "frac": achieved / peak,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.genome_mb == 135.0 and world == 1) else None,
+                "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, N=1 full-size launch)",
                 "peak_source": "mg_microbench on this GPU: LOP3 %.0f Glane-op/s, LDS.32 %.0f Glane-op/s" % (lop3, lds),
-                "ceilings_tcell_s": {"lsu_shared": peak_lsu, "alu_lop3": peak_alu},
+                "work_per_step": {"second_stage_fraction": f2, "lds_per_lane": loads_per_step, "alu_per_lane": alu_per_step},
+                "ceilings_tcell_s": {"lsu_shared": peak_lsu, "alu_lop3": peak_alu, "lsu_without_early_out": brute},
+                "frac_of_ceiling_without_early_out": achieved / brute,
                 "kernel": "screen_bitsliced_kernel<20,4,1024>", "kernel_ms": kern_ms,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_gbs": alg_bytes / (kern_ms / 1e3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),

@@ -35,6 +35,7 @@ typedef enum {
 #define MG_MAX_PATTERN_UNITS 32
 #define MG_MAX_PATTERN_OPS 96
 #define MG_MAX_GAPS 3
+#define MG_MAX_PIECES 8
 
 const char* mg_last_error(void);
 int mg_version(void);
@@ -146,6 +147,12 @@ typedef struct {
     mg_pattern_unit units[MG_MAX_PATTERN_UNITS];
     int32_t ops[MG_MAX_PATTERN_OPS];
     int32_t prefilter_edits;  /* host-derived bound: pattern true => full-length edit cost <= this; <0 = unbounded */
+    /* Optional exact-piece prefilter for patterns (pigeonhole): the host proves that every alignment satisfying
+     * the pattern matches the subject EXACTLY, without gaps, on at least one of these gRNA position ranges
+     * (in gRNA orientation).  n_pieces = 0: not used. */
+    int32_t n_pieces;
+    int32_t piece_start[MG_MAX_PIECES];
+    int32_t piece_len[MG_MAX_PIECES];
 } mg_criteria;
 
 /* K4/K5 - exhaustive off-target screen of every resident gRNA against every window of the genome, both
@@ -169,6 +176,11 @@ int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
 /* Layout of the global coordinate space (for sharding by chunk with a halo): global start of a contig. */
 int64_t mg_genome_contig_global_start(const mg_genome* g, int contig);
 int64_t mg_genome_global_length(const mg_genome* g);
+
+/* Work actually executed by the most recent bit-sliced scan launch on this device (synchronises):
+ * out[0] = (warp, 32-query group) steps, out[1] = how many of them went past the early-out test, i.e. also
+ * loaded and summed the last quarter of the gRNA positions.  Used by bench.py for the roofline accounting. */
+int mg_last_screen_stats(uint64_t* out /* [2] */);
 
 /* Integer-pipe microbenchmarks used for the roofline denominators of the scan kernel (bench.py):
  * which: 0 = LOP3 (ALU pipe) lane-ops, 1 = shared-memory 32-bit loads (LSU).  Returns Gops/s in *gops. */

@@ -14,6 +14,7 @@ MG_MAX_PAM_ALTS = 32
 MG_MAX_PATTERN_UNITS = 32
 MG_MAX_PATTERN_OPS = 96
 MG_MAX_GAPS = 3
+MG_MAX_PIECES = 8
 MG_OP_AND, MG_OP_OR = -1, -2
 MG_CH_MISMATCH, MG_CH_INS, MG_CH_DEL = 1, 2, 4
 MG_SLICE_NONE = -(2 ** 31)
@@ -25,7 +26,7 @@ EXPORTS = [
     "mg_genome_total_bases", "mg_genome_device_bytes", "mg_genome_decode", "mg_genome_free", "mg_genome_set_masks",
     "mg_mask_find", "mg_enumerate_sites", "mg_queries_create", "mg_queries_count", "mg_queries_length",
     "mg_queries_free", "mg_screen", "mg_screen_host", "mg_genome_contig_global_start", "mg_genome_global_length",
-    "mg_microbench",
+    "mg_microbench", "mg_last_screen_stats",
 ]
 
 
@@ -52,7 +53,8 @@ class PatternUnit(C.Structure):
 class Criteria(C.Structure):
     _fields_ = [("max_mismatch", C.c_int32), ("max_gap", C.c_int32), ("pamless", C.c_int32), ("n_units", C.c_int32),
                 ("n_ops", C.c_int32), ("units", PatternUnit * MG_MAX_PATTERN_UNITS), ("ops", C.c_int32 * MG_MAX_PATTERN_OPS),
-                ("prefilter_edits", C.c_int32)]
+                ("prefilter_edits", C.c_int32), ("n_pieces", C.c_int32), ("piece_start", C.c_int32 * MG_MAX_PIECES),
+                ("piece_len", C.c_int32 * MG_MAX_PIECES)]
 
 
 _lib = None
@@ -98,6 +100,7 @@ def lib():
     L.mg_screen_host.argtypes = [vp, i64p, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(Criteria),
                                  C.POINTER(Pam), vp, vp]
     L.mg_microbench.argtypes = [C.c_int, C.POINTER(C.c_double), vp]
+    L.mg_last_screen_stats.argtypes = [C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -315,3 +318,10 @@ def microbench(which, stream=0):
     v = C.c_double(0)
     check(lib().mg_microbench(int(which), C.byref(v), C.c_void_p(stream)), "mg_microbench")
     return float(v.value)
+
+
+def last_screen_stats():
+    """(steps, second-stage steps) of the most recent bit-sliced scan launch (see mg_last_screen_stats)."""
+    out = (C.c_uint64 * 2)()
+    check(lib().mg_last_screen_stats(out), "mg_last_screen_stats")
+    return int(out[0]), int(out[1])

@@ -7,6 +7,8 @@ using namespace mg;
 
 namespace mg {
 
+int screen_stats(unsigned long long out[2]);
+
 // ---------------------------------------------------------------- integer-pipe microbenchmarks
 // Denominators for the scan kernel's roofline (MEASURED_PEAKS.json only has HBM and bf16 numbers).
 __global__ void __launch_bounds__(1024, 1) ubench_lop3(uint32_t* out, int iters) {
@@ -49,6 +51,14 @@ __global__ void __launch_bounds__(1024, 1) ubench_lds(uint32_t* out, int iters) 
 }  // namespace mg
 
 extern "C" {
+
+int mg_last_screen_stats(uint64_t* out) {
+    MG_CHECK_ARG(out != nullptr);
+    unsigned long long tmp[2];
+    const int rc = screen_stats(tmp);
+    out[0] = tmp[0]; out[1] = tmp[1];
+    return rc;
+}
 
 int mg_microbench(int which, double* gops, void* stream) {
     MG_CHECK_ARG(gops != nullptr && (which == 0 || which == 1));

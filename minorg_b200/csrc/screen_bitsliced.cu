@@ -83,7 +83,8 @@ __device__ __noinline__ void verify_hits(const GenomeView& gv, const QueriesView
 template <int L, int K, int THREADS, bool GENERAL, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chunk, int64_t wb, int64_t we,
-                        uint32_t* __restrict__ counts, const GeneralCtx* __restrict__ gctx) {
+                        uint32_t* __restrict__ counts, const GeneralCtx* __restrict__ gctx,
+                        unsigned long long* __restrict__ stats) {
     constexpr int S = 4 * L + 1;                     // table words per group
     constexpr int NB = mgcsa::CountBits<L>::value;
     constexpr int T1 = SPLIT ? mgcsa::SplitOf<L>::value : 0;      // positions summed before the early-out test
@@ -96,6 +97,7 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
     per = (per + 31) / 32 * 32;
     const int64_t w0 = wb + (int64_t)blockIdx.x * per;
     const int64_t w1 = min(we, w0 + per);
+    unsigned int n_steps = 0, n_stage2 = 0;       // per-warp tallies of (warp, group) steps / second stages
 
     for (int cg = 0; cg < qv.n_groups; cg += groups_per_chunk) {
         const int ng = min(groups_per_chunk, qv.n_groups - cg);
@@ -135,7 +137,9 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
                     uint32_t part[NB1];
                     mgcsa::csa_count<T1>(x1, part);
                     const uint32_t alive = (K >= 0) ? le_const_impl<NB1>(part, K) : le_runtime<NB1>(part, kthr);
+                    ++n_steps;
                     if (!__any_sync(0xFFFFFFFFu, alive != 0u)) continue;
+                    ++n_stage2;
                     uint32_t x2[L - T1];
 #pragma unroll
                     for (int j = T1; j < L; ++j) x2[j - T1] = *reinterpret_cast<const uint32_t*>(t + off[j]);
@@ -157,6 +161,20 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
             }
         }
     }
+    if (stats != nullptr && (threadIdx.x & 31) == 0) {
+        atomicAdd(stats, (unsigned long long)n_steps);
+        atomicAdd(stats + 1, (unsigned long long)n_stage2);
+    }
+}
+
+// [0] (warp, query-group) steps, [1] steps that needed the second stage - of the most recent launch
+static unsigned long long* g_stats = nullptr;
+
+int screen_stats(unsigned long long out[2]) {
+    out[0] = out[1] = 0;
+    if (!g_stats) return MG_OK;
+    MG_CUDA(cudaMemcpy(out, g_stats, 16, cudaMemcpyDeviceToHost));
+    return MG_OK;
 }
 
 template <int L, int K, bool GENERAL = false>
@@ -177,7 +195,9 @@ static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t
     int64_t grid = (nwin + THREADS - 1) / THREADS;
     if (grid > sms) grid = sms;             // persistent: one CTA per SM, each owns a contiguous genome slice
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts, gctx);
+    if (!g_stats) MG_CUDA(cudaMalloc(&g_stats, 16));
+    MG_CUDA(cudaMemsetAsync(g_stats, 0, 16, s));
+    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts, gctx, g_stats);
     MG_CUDA(cudaGetLastError());
     return MG_OK;
 }

@@ -73,6 +73,71 @@ myers_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, 
     }
 }
 
+// ----------------------------------------------------------------------------------------- exact pieces
+// Pigeonhole prefilter for patterns (host proof: ot_regex.OffTargetExpression.exact_pieces): a query survives at
+// window p iff it matches the subject exactly on one of the given position ranges.  Same bit-sliced tables as
+// the scan kernel (OR of the mismatch words of a range == 0).  A gap after (before) the matching range moves
+// the alignment's virtual end by at most Gp, so 2*Gp+1 anchors go to the exact verifier.
+constexpr int kPieceThreads = 512;
+
+__global__ void __launch_bounds__(kPieceThreads)
+pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, int groups_per_chunk, int64_t wb,
+              int64_t we, uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t tab[];
+    const int L = qv.len, S = 4 * L + 1, N = qv.n;
+    const int n_pieces = ctx->n_pieces, Gp = ctx->Gp;
+    for (int cg = 0; cg < qv.n_groups; cg += groups_per_chunk) {
+        const int ng = min(groups_per_chunk, qv.n_groups - cg);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ng * S; i += blockDim.x) tab[i] = __ldg(qv.tab + (size_t)cg * S + i);
+        __syncthreads();
+        for (int64_t p = wb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < we; p += (int64_t)gridDim.x * blockDim.x) {
+            uint32_t lo, hi, inv;
+            load_window(gv, p, lo, hi, inv);
+            uint32_t off[MG_MAX_GRNA_LEN];
+#pragma unroll
+            for (int j = 0; j < MG_MAX_GRNA_LEN; ++j) {
+                const uint32_t code = (j < 16) ? ((lo >> (2 * j)) & 3u) : ((hi >> (2 * (j - 16))) & 3u);
+                off[j] = (j < L) ? ((((inv >> j) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * j) + code)) : (uint32_t)(4 * L);
+            }
+            for (int g = 0; g < ng; ++g) {
+                const uint32_t* t = tab + (size_t)g * S;
+                // a group is entirely '+' queries, entirely '-' (reverse-complement) queries, or straddles N
+                const int q0 = (cg + g) * 32;
+                uint32_t hit = 0u;
+                for (int k = 0; k < n_pieces; ++k) {
+                    const uint32_t mf = ctx->piece_fwd[k], mr = ctx->piece_rev[k];
+                    uint32_t accf = 0u, accr = 0u;
+#pragma unroll
+                    for (int j = 0; j < MG_MAX_GRNA_LEN; ++j) {
+                        if (((mf | mr) >> j) & 1u) {
+                            const uint32_t w = t[off[j]];
+                            if ((mf >> j) & 1u) accf |= w;
+                            if ((mr >> j) & 1u) accr |= w;
+                        }
+                    }
+                    // bit i belongs to query q0+i: '+' orientation uses the forward mask, '-' the mirrored one
+                    uint32_t plus_bits = 0u;
+                    if (q0 + 32 <= N) plus_bits = 0xFFFFFFFFu;
+                    else if (q0 < N) plus_bits = (1u << (N - q0)) - 1u;
+                    hit |= (~accf & plus_bits) | (~accr & ~plus_bits);
+                }
+                while (hit) {
+                    const int i = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const int q = q0 + i;
+                    if (q >= 2 * N) continue;
+                    const int gi = q < N ? q : q - N;
+                    const int strand = q < N ? 1 : -1;
+                    const int64_t e0 = strand > 0 ? p + L : gv.glen - p;
+                    for (int d = -Gp; d <= Gp; ++d)
+                        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, strand, e0 + d)) atomicAdd(counts + q, 1u);
+                }
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------- every cell
 __global__ void __launch_bounds__(128)
 allcells_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, int strand, int64_t eb, int64_t ee,
@@ -124,6 +189,18 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         h.five_max = pam->five_maxlen;
         h.three_max = pam->three_maxlen;
     }
+    MG_CHECK_ARG(crit->n_pieces >= 0 && crit->n_pieces <= MG_MAX_PIECES);
+    h.n_pieces = crit->n_units ? crit->n_pieces : 0;
+    for (int k = 0; k < h.n_pieces; ++k) {
+        const int a = crit->piece_start[k], n = crit->piece_len[k];
+        MG_CHECK_ARG(a >= 0 && n >= 1 && a + n <= L);
+        uint32_t m = 0;
+        for (int j = a; j < a + n; ++j) m |= 1u << j;
+        uint32_t r = 0;
+        for (int j = a; j < a + n; ++j) r |= 1u << (L - 1 - j);      // the same bases in a reverse-complemented query
+        h.piece_fwd[k] = m;
+        h.piece_rev[k] = r;
+    }
     GeneralCtx* d_ctx = nullptr;
     MG_CUDA(cudaMalloc(&d_ctx, sizeof h));
     int rc = MG_OK;
@@ -138,7 +215,21 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     // strand -1 anchors: a window [p, p+L) of the forward genome ends, in reverse-complement coordinates, at
     // glen - p; the shard [wb, we) therefore owns e' in [glen - we + 1, glen - wb + 1)
     const int64_t mb = g->glen - we + 1, me = g->glen - wb + 1;
-    if (crit->max_gap == 0 && K >= 0) {
+    if (h.n_pieces > 0) {
+        int dev = 0, sms = 0, smem_max = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const int S = 4 * L + 1;
+        const int max_groups = (smem_max - 1024) / (S * 4);
+        const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
+        const size_t smem = (size_t)gpc * S * 4;
+        cudaFuncSetAttribute(pieces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int64_t grid = (we - wb + kPieceThreads - 1) / kPieceThreads;
+        if (grid > sms) grid = sms;
+        if (grid < 1) grid = 1;
+        pieces_kernel<<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, gpc, wb, we, d_counts);
+    } else if (crit->max_gap == 0 && K >= 0) {
         rc = launch_screen_bitsliced_general(g, q, K, d_ctx, wb, we, d_counts, s);
     } else {
         for (int z = 0; z < 2; ++z) {

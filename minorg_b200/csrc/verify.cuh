@@ -32,6 +32,8 @@ struct GeneralCtx {
     PamSideDev five, three;
     int32_t five_max, three_max;
     int32_t prune_pattern;    // 1: partial pattern evaluation is a sound lower bound (Gp <= 1: no 'dd' elements)
+    int32_t n_pieces;         // exact-piece prefilter: position masks in gRNA orientation and mirrored (rc queries)
+    uint32_t piece_fwd[MG_MAX_PIECES], piece_rev[MG_MAX_PIECES];
 };
 
 // Python slice [start:end:step] with concrete bounds on a sequence of n elements; step = +1 if end >= start

@@ -256,6 +256,45 @@ class OffTargetExpression:
             worst = max(worst, best)
         return worst
 
+    def exact_pieces(self, length, max_gap, min_piece=None):
+        """Pigeonhole prefilter: gRNA position ranges [(start, len)] such that every alignment satisfying the
+        pattern matches the subject exactly and gap-free on at least one of them, or None if no such set of
+        useful (>= min_piece bases) ranges can be proven.  For each clause of the disjunctive normal form take
+        the unit 'n m.. <range>' (counting unaligned positions as mismatches) whose range holds the longest
+        run R of consecutive positions: at most n errors (+ max_gap if it ignores a gap type) fall inside R,
+        so one of n_eff + 1 equal parts of R is error-free.  Only for max_gap <= 1 (no 'dd' tuple elements, so
+        tuple index == gRNA position, blast.py:102-117)."""
+        if max_gap > 1:
+            return None
+        if min_piece is None:
+            min_piece = max(5, min(8, length // 2))     # 4^-8 survivors per cell at L >= 16
+        pieces = []
+        for clause in self.clauses():
+            best = None
+            for u in clause:
+                if not (u.mismatch and self.unaligned_as_mismatch):
+                    continue
+                a = 0 if u.start is None else u.start
+                b = length if u.end is None else u.end
+                idx = sorted(list(range(length))[a:b:(1 if b >= a else -1)])
+                run, cur = [], []
+                for i in idx:                      # longest run of consecutive positions
+                    cur = cur + [i] if cur and i == cur[-1] + 1 else [i]
+                    if len(cur) > len(run):
+                        run = cur
+                if not run:
+                    continue
+                n_eff = u.n + (0 if (u.gap or (u.ins and u.dele)) else max_gap)
+                part = len(run) // (n_eff + 1)
+                if part >= min_piece and (best is None or part > best[0]):
+                    best = (part, run[0], n_eff + 1)
+            if best is None:
+                return None
+            part, first, k = best
+            pieces.extend((first + i * part, part) for i in range(k))
+        pieces = sorted(set(pieces))
+        return pieces if 0 < len(pieces) <= _lib.MG_MAX_PIECES else None
+
     def clauses(self):
         """Disjunctive normal form: list of clauses, each a list of units (the tree has only AND/OR)."""
         def walk(node):
@@ -286,4 +325,10 @@ def make_criteria(ot_mismatch=1, ot_gap=0, ot_pattern=None, ot_unaligned_as_mism
         expr.lower(c)
         if grna_length is not None:
             c.prefilter_edits = expr.edit_bound(int(grna_length), c.max_gap)
+            pieces = expr.exact_pieces(int(grna_length), c.max_gap)
+            # without gaps a finite Hamming budget is the tighter prefilter; pieces serve gapped / unbounded patterns
+            if pieces and (c.max_gap > 0 or c.prefilter_edits < 0):
+                c.n_pieces = len(pieces)
+                for i, (a, n) in enumerate(pieces):
+                    c.piece_start[i], c.piece_len[i] = a, n
     return c

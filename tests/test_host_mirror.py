@@ -86,3 +86,59 @@ def test_criteria_lowering():
     assert (c.units[2].start, c.units[2].end, c.units[2].rvs, c.units[2].n) == (-2, -3, 1, 2)
     assert c.units[1].start == 5 and c.units[1].end == -(2 ** 31)
     assert R.make_criteria(0, 0).max_mismatch == 0 and R.make_criteria(1, 1).max_gap == 0
+
+
+def _random_alignment(rng, L, max_gap):
+    """kinds string + (qs, qe) of a random member of the alignment universe."""
+    qs = rng.choice([0, 0, 0, 1, 2, 3])
+    qe = L - rng.choice([0, 0, 0, 1, 2, 3])
+    kinds, gaps, j = [], 0, qs
+    while j < qe:
+        first, last = j == qs, j == qe - 1
+        r = rng.random()
+        if not first and gaps < max_gap and r < 0.05:
+            kinds.append("d"); gaps += 1
+            continue
+        if not first and not last and gaps < max_gap and r < 0.10:
+            kinds.append("i"); gaps += 1; j += 1
+            continue
+        kinds.append("m" if r > 0.85 else "."); j += 1
+    return "".join(kinds), qs, qe
+
+
+def test_prefilter_bounds_are_sound():
+    """edit_bound / exact_pieces must be NECESSARY conditions of the pattern (the device prefilters rely on it):
+    checked by brute force on random alignments evaluated with the oracle's tuple semantics."""
+    import random
+    rng = random.Random(99)
+    L = 20
+    pats = ["0mg-10,1mg-11-", "1mg1-", "2mg1-", "0mg5,1mg6-", "(0mg5,1mg6-)|(0mg6,1m7-)", "1m10,1m11-", "1m1-,1g1-",
+            "0mg-12|0mg12", "1mg-14", "0m-9,3mg1-", "2m1-", "0mg8,0mg-8"]
+    checked = 0
+    for pat in pats:
+        for gcap in (0, 1):
+            e = R.OffTargetExpression(pat)
+            bound = e.edit_bound(L, gcap)
+            pieces = e.exact_pieces(L, gcap)
+            for _ in range(1500):
+                kinds, qs, qe = _random_alignment(rng, L, gcap)
+                aln = O.Alignment(kinds, qs, qe, L)
+                if not e(_HSP(aln)):
+                    continue
+                checked += 1
+                cost = aln.mismatches + aln.gaps + (L - (qe - qs))
+                if bound >= 0:
+                    assert cost <= bound, (pat, gcap, kinds, qs, qe)
+                if pieces:
+                    # per query position: '.', 'm', 'i' or ' ' and whether a deletion touches it
+                    per, dele, j = [" "] * L, [False] * (L + 1), qs
+                    for ch in kinds:
+                        if ch == "d":
+                            dele[j] = True
+                        else:
+                            per[j] = ch
+                            j += 1
+                    ok = any(all(per[x] == "." for x in range(a, a + n)) and not any(dele[x] for x in range(a + 1, a + n))
+                             for a, n in pieces)
+                    assert ok, (pat, gcap, kinds, qs, qe, pieces)
+    assert checked > 1000
