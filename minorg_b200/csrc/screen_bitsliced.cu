@@ -63,20 +63,17 @@ __device__ __noinline__ void report_hits(const GenomeView& gv, int n_queries, in
     }
 }
 
-// Cold path of the general screen: the Hamming budget is only a prefilter; each survivor is an anchor for the
-// exact verifier (verify.cuh).  Query q < N is gRNA q on the '+' strand, q >= N its reverse complement, i.e.
+// Cold path of the general screen: the Hamming budget is only a prefilter; each survivor is queued as an anchor
+// for the exact verifier pass (verify.cuh, screen_general.cu).  Query q < N is gRNA q on the '+' strand, q >= N its reverse complement, i.e.
 // gRNA q-N on the '-' strand, whose window [p, p+L) ends at glen - p in reverse-complement coordinates.
 __device__ __noinline__ void verify_hits(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* ctx, uint32_t hit,
-                                         int group, int64_t p, uint32_t* __restrict__ counts) {
+                                         int group, int64_t p) {
     while (hit) {
         const int i = __ffs(hit) - 1;
         hit &= hit - 1;
         const int q = group * 32 + i;
         if (q >= 2 * qv.n) continue;
-        const int gi = q < qv.n ? q : q - qv.n;
-        const int strand = q < qv.n ? 1 : -1;
-        const int64_t e = strand > 0 ? p + qv.len : gv.glen - p;
-        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * qv.len, strand, e)) atomicAdd(counts + q, 1u);
+        emit_candidate(*ctx, q, q < qv.n ? p + qv.len : gv.glen - p);
     }
 }
 
@@ -155,7 +152,7 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
                     hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
                 }
                 if (hit) {
-                    if (GENERAL) verify_hits(gv, qv, gctx, hit, cg + g, p, counts);
+                    if (GENERAL) verify_hits(gv, qv, gctx, hit, cg + g, p);
                     else report_hits(gv, 2 * qv.n, L, hit, cg + g, p, counts);
                 }
             }
@@ -241,12 +238,21 @@ int launch_screen_bitsliced_general(const mg_genome* g, const mg_queries* q, int
     if (q->n == 0 || we <= wb) return MG_OK;
     switch (q->len) {
 #define MG_CASE_GEN(LL) case LL: return launch_one<LL, -1, true>(g, q, k, wb, we, d_counts, s, d_ctx);
+#define MG_CASE_GEN_K(LL) case LL: switch (k) {                                                   \
+            case 0: return launch_one<LL, 0, true>(g, q, k, wb, we, d_counts, s, d_ctx);            \
+            case 1: return launch_one<LL, 1, true>(g, q, k, wb, we, d_counts, s, d_ctx);            \
+            case 2: return launch_one<LL, 2, true>(g, q, k, wb, we, d_counts, s, d_ctx);            \
+            case 3: return launch_one<LL, 3, true>(g, q, k, wb, we, d_counts, s, d_ctx);            \
+            case 4: return launch_one<LL, 4, true>(g, q, k, wb, we, d_counts, s, d_ctx);            \
+            case 5: return launch_one<LL, 5, true>(g, q, k, wb, we, d_counts, s, d_ctx);            \
+            default: return launch_one<LL, -1, true>(g, q, k, wb, we, d_counts, s, d_ctx); }
         MG_CASE_GEN(1) MG_CASE_GEN(2) MG_CASE_GEN(3) MG_CASE_GEN(4) MG_CASE_GEN(5) MG_CASE_GEN(6) MG_CASE_GEN(7) MG_CASE_GEN(8)
         MG_CASE_GEN(9) MG_CASE_GEN(10) MG_CASE_GEN(11) MG_CASE_GEN(12) MG_CASE_GEN(13) MG_CASE_GEN(14) MG_CASE_GEN(15)
-        MG_CASE_GEN(16) MG_CASE_GEN(17) MG_CASE_GEN(18) MG_CASE_GEN(19) MG_CASE_GEN(20) MG_CASE_GEN(21) MG_CASE_GEN(22)
-        MG_CASE_GEN(23) MG_CASE_GEN(24) MG_CASE_GEN(25) MG_CASE_GEN(26) MG_CASE_GEN(27) MG_CASE_GEN(28) MG_CASE_GEN(29)
+        MG_CASE_GEN(16) MG_CASE_GEN(17) MG_CASE_GEN(18) MG_CASE_GEN(19) MG_CASE_GEN_K(20) MG_CASE_GEN(21) MG_CASE_GEN(22)
+        MG_CASE_GEN_K(23) MG_CASE_GEN(24) MG_CASE_GEN(25) MG_CASE_GEN(26) MG_CASE_GEN(27) MG_CASE_GEN(28) MG_CASE_GEN(29)
         MG_CASE_GEN(30) MG_CASE_GEN(31) MG_CASE_GEN(32)
 #undef MG_CASE_GEN
+#undef MG_CASE_GEN_K
         default: set_error("gRNA length %d unsupported (1..32)", q->len); return MG_ERR_UNSUPPORTED;
     }
 }

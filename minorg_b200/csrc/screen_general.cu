@@ -65,11 +65,7 @@ myers_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, 
         Mh <<= 1;
         Pv = Mh | ~(Xv | Ph);
         Mv = Ph & Xv;
-        if (score <= K && i >= warm) {
-            const int64_t e = from + i + 1;
-            if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, strand, e))
-                atomicAdd(counts + (strand > 0 ? gi : N + gi), 1u);
-        }
+        if (score <= K && i >= warm) emit_candidate(*ctx, strand > 0 ? gi : N + gi, from + i + 1);
     }
 }
 
@@ -127,15 +123,23 @@ pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx,
                     hit &= hit - 1;
                     const int q = q0 + i;
                     if (q >= 2 * N) continue;
-                    const int gi = q < N ? q : q - N;
-                    const int strand = q < N ? 1 : -1;
-                    const int64_t e0 = strand > 0 ? p + L : gv.glen - p;
-                    for (int d = -Gp; d <= Gp; ++d)
-                        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, strand, e0 + d)) atomicAdd(counts + q, 1u);
+                    const int64_t e0 = q < N ? p + L : gv.glen - p;
+                    for (int d = -Gp; d <= Gp; ++d) emit_candidate(*ctx, q, e0 + d);
                 }
             }
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------- verifier pass
+__global__ void __launch_bounds__(128)
+verify_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, unsigned long long n_cand,
+              uint32_t* __restrict__ counts) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const Cand c = ctx->cand[i];
+    const int gi = c.q < qv.n ? c.q : c.q - qv.n;
+    if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * qv.len, c.q < qv.n ? 1 : -1, c.e)) atomicAdd(counts + c.q, 1u);
 }
 
 // ----------------------------------------------------------------------------------------- every cell
@@ -201,54 +205,100 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         h.piece_fwd[k] = m;
         h.piece_rev[k] = r;
     }
+    // candidate queue between the prefilter and the verifier pass
+    h.cand_cap = 16ull << 20;
+    MG_CUDA(dev_alloc((void**)&h.cand, sizeof(Cand) * h.cand_cap, s));
+    MG_CUDA(dev_alloc((void**)&h.cand_count, 8, s));
+    MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
     GeneralCtx* d_ctx = nullptr;
     MG_CUDA(cudaMalloc(&d_ctx, sizeof h));
     int rc = MG_OK;
     cudaError_t e = cudaMemcpyAsync(d_ctx, &h, sizeof h, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);     // h is on this stack frame
-    if (e != cudaSuccess) { cudaFree(d_ctx); set_error("copying criteria: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    if (e != cudaSuccess) { cudaFree(d_ctx); dev_free(h.cand, s); dev_free(h.cand_count, s); set_error("copying criteria: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
 
     // anchors (virtual ends, exclusive) owned by the window range [wb, we): e = p + L
-    const int64_t eb = wb + L, ee = we + L;
     int K = crit->n_units ? crit->prefilter_edits : crit->max_mismatch + crit->max_gap;
     if (K >= L) K = -1;
-    // strand -1 anchors: a window [p, p+L) of the forward genome ends, in reverse-complement coordinates, at
-    // glen - p; the shard [wb, we) therefore owns e' in [glen - we + 1, glen - wb + 1)
-    const int64_t mb = g->glen - we + 1, me = g->glen - wb + 1;
-    if (h.n_pieces > 0) {
-        int dev = 0, sms = 0, smem_max = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        const int S = 4 * L + 1;
-        const int max_groups = (smem_max - 1024) / (S * 4);
-        const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
-        const size_t smem = (size_t)gpc * S * 4;
-        cudaFuncSetAttribute(pieces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int64_t grid = (we - wb + kPieceThreads - 1) / kPieceThreads;
-        if (grid > sms) grid = sms;
-        if (grid < 1) grid = 1;
-        pieces_kernel<<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, gpc, wb, we, d_counts);
-    } else if (crit->max_gap == 0 && K >= 0) {
-        rc = launch_screen_bitsliced_general(g, q, K, d_ctx, wb, we, d_counts, s);
-    } else {
+    const bool by_pieces = h.n_pieces > 0;
+    const bool by_hamming = !by_pieces && crit->max_gap == 0 && K >= 0;
+    const bool by_myers = !by_pieces && !by_hamming && K >= 0;
+    int dev = 0, sms = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+
+    // prefilter over windows [a, b): queues survivors.  strand -1 anchors of a window [p, p+L) end, in
+    // reverse-complement coordinates, at glen - p; so windows [a, b) own e' in [glen - b + 1, glen - a + 1).
+    auto prefilter = [&](int64_t a, int64_t b) -> int {
+        if (by_pieces) {
+            const int S = 4 * L + 1;
+            const int max_groups = (smem_max - 1024) / (S * 4);
+            const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
+            const size_t smem = (size_t)gpc * S * 4;
+            cudaFuncSetAttribute(pieces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int64_t grid = (b - a + kPieceThreads - 1) / kPieceThreads;
+            if (grid > sms) grid = sms;
+            pieces_kernel<<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, gpc, a, b, d_counts);
+            return MG_OK;
+        }
+        if (by_hamming) return launch_screen_bitsliced_general(g, q, K, d_ctx, a, b, d_counts, s);
         for (int z = 0; z < 2; ++z) {
             const int strand = z == 0 ? 1 : -1;
-            const int64_t b = z == 0 ? eb : mb, en = z == 0 ? ee : me;
-            const int64_t n_anchor = en - b;
+            const int64_t eb = z == 0 ? a + L : g->glen - b + 1, ee = z == 0 ? b + L : g->glen - a + 1;
+            const int64_t n_anchor = ee - eb;
             if (n_anchor <= 0) continue;
-            if (K < 0) {
-                int64_t grid = (n_anchor * q->n + 127) / 128;
-                if (grid > 148 * 16) grid = 148 * 16;
-                allcells_kernel<<<(unsigned)grid, 128, 0, s>>>(g->view(), q->view(), d_ctx, strand, b, en, d_counts);
-            } else {
+            if (by_myers) {
                 dim3 grid((unsigned)((n_anchor + kMyersChunk - 1) / kMyersChunk), (unsigned)((q->n + kMyersThreads - 1) / kMyersThreads), 1);
-                myers_kernel<<<grid, kMyersThreads, 0, s>>>(g->view(), q->view(), d_ctx, K, strand, b, en, d_counts);
+                myers_kernel<<<grid, kMyersThreads, 0, s>>>(g->view(), q->view(), d_ctx, K, strand, eb, ee, d_counts);
+            } else {
+                int64_t grid = (n_anchor * q->n + 127) / 128;
+                if (grid > sms * 16) grid = sms * 16;
+                allcells_kernel<<<(unsigned)grid, 128, 0, s>>>(g->view(), q->view(), d_ctx, strand, eb, ee, d_counts);
             }
         }
+        return MG_OK;
+    };
+
+    // Run [wb, we) in slices whose survivors fit the queue; an overflowing slice is re-run in as many parts as
+    // its survivor count calls for (nothing of it has been verified yet, so no double counting).
+    std::vector<std::pair<int64_t, int64_t>> todo;
+    todo.emplace_back(wb, we);
+    unsigned long long total_cand = 0;
+    while (!todo.empty() && rc == MG_OK) {
+        const std::pair<int64_t, int64_t> r = todo.back();
+        todo.pop_back();
+        if (r.second <= r.first) continue;
+        MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
+        rc = prefilter(r.first, r.second);
+        if (rc != MG_OK) break;
+        unsigned long long n_cand = 0;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&n_cand, h.cand_count, 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) break;
+        if (n_cand > h.cand_cap) {
+            const int64_t len = r.second - r.first;
+            if (len <= 1) { set_error("candidate queue too small for a single window (%llu survivors)", n_cand); rc = MG_ERR_NOMEM; break; }
+            int64_t parts = (int64_t)((n_cand + h.cand_cap / 2 - 1) / (h.cand_cap / 2));
+            if (parts > len) parts = len;
+            if (parts < 2) parts = 2;
+            for (int64_t i = parts - 1; i >= 0; --i)
+                todo.emplace_back(r.first + len * i / parts, r.first + len * (i + 1) / parts);
+            continue;
+        }
+        total_cand += n_cand;
+        if (n_cand > 0) {
+            verify_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, s>>>(g->view(), q->view(), d_ctx, n_cand, d_counts);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) break;
+        }
     }
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);     // d_ctx must outlive the kernels
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // d_ctx and the queue must outlive the kernels
+    if (getenv("MG_TRACE")) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu\n",
+                                    by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? "myers" : "all-cells", K, total_cand);
+    dev_free(h.cand, s);
+    dev_free(h.cand_count, s);
     cudaFree(d_ctx);
     if (e != cudaSuccess) { set_error("general screen: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     return rc;

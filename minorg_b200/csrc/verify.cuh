@@ -34,6 +34,17 @@ struct GeneralCtx {
     int32_t prune_pattern;    // 1: partial pattern evaluation is a sound lower bound (Gp <= 1: no 'dd' elements)
     int32_t n_pieces;         // exact-piece prefilter: position masks in gRNA orientation and mirrored (rc queries)
     uint32_t piece_fwd[MG_MAX_PIECES], piece_rev[MG_MAX_PIECES];
+    // prefilter survivors are queued here and verified by a second kernel with one thread per candidate
+    // (verifying inline would run one lane of a warp at a time and drag a 2 KB stack into the scan kernel)
+    struct Cand* cand;
+    unsigned long long* cand_count;
+    unsigned long long cand_cap;
+};
+
+struct Cand {
+    int32_t q;        // oriented query index: q < N = gRNA q on '+', q >= N = gRNA q-N on '-'
+    int32_t pad;
+    int64_t e;        // anchor: virtual end of the alignment in strand coordinates
 };
 
 // Python slice [start:end:step] with concrete bounds on a sequence of n elements; step = +1 if end >= start
@@ -198,6 +209,79 @@ __device__ inline bool partial_may_succeed(const GeneralCtx& c, const AlnState& 
     return pattern_true(c, a, tail);
 }
 
+// Closed-form verifier for the no-pattern criterion with at most ONE gap character (the reference's default
+// and the common --ot-gap 2 case).  With <= 1 gap an alignment ending (virtually) at e is: a stretch of the main
+// diagonal D0; or a prefix on the neighbouring diagonal D-1 joined to D0 by a deletion before query position k;
+// or a prefix on D+1 joined by an insertion AT position k.  Mismatch bit-masks of the three diagonals turn every
+// (qs, qe, k) choice into two popcounts, instead of the column-by-column search below.
+__device__ inline uint32_t bit_range(int a, int b) {      // bits [a, b), 0 <= a <= b <= 32
+    const uint32_t hi = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    const uint32_t lo = a >= 32 ? 0xFFFFFFFFu : ((1u << a) - 1u);
+    return hi & ~lo;
+}
+
+__device__ inline bool verify_nopattern_one_gap(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
+                                                int strand, int64_t e, int64_t cs, int64_t ce) {
+    const int L = c.L;
+    const int64_t base = e - L;                            // D0: query position j <-> subject base + j
+    uint32_t m0 = 0, mM = 0, mP = 0, f0 = 0, fM = 0, fP = 0;   // mismatch / off-contig masks per diagonal
+    int prev = -1, cur = -1, next = -1;
+    {
+        const int64_t x0 = base - 1, x1 = base;
+        prev = (x0 >= cs && x0 < ce) ? tbase(gv, strand, x0) : -1;
+        cur = (x1 >= cs && x1 < ce) ? tbase(gv, strand, x1) : -1;
+    }
+    for (int j = 0; j < L; ++j) {
+        const int64_t x2 = base + j + 1;
+        next = (x2 >= cs && x2 < ce) ? tbase(gv, strand, x2) : -1;
+        const int qb = q[j];
+        const uint32_t b = 1u << j;
+        if (cur < 0) f0 |= b;
+        if (prev < 0) fM |= b;
+        if (next < 0) fP |= b;
+        if (qb >= 4 || qb != cur) m0 |= b;
+        if (qb >= 4 || qb != prev) mM |= b;
+        if (qb >= 4 || qb != next) mP |= b;
+        prev = cur;
+        cur = next;
+    }
+    const int B = c.M + c.Gp;
+    for (int qe = L; qe >= 1 && L - qe <= B; --qe) {
+        const int trim3 = L - qe;
+        for (int qs = 0; qs < qe && trim3 + qs <= B; ++qs) {          // no gap
+            const uint32_t r = bit_range(qs, qe);
+            if (f0 & r) continue;
+            const int mm = __popc(m0 & r);
+            if (mm > c.M || mm + trim3 + qs > B) continue;
+            const AlnState a{m0 & r, 0u, 0u, 0u, mm, 0};
+            if (alignment_problematic(gv, c, strand, a, qs, qe, base + qs, base + qe, cs, ce)) return true;
+        }
+        if (c.Gp < 1) continue;
+        for (int qs = 0; qs < qe && trim3 + qs + 1 <= B; ++qs) {
+            const int u = trim3 + qs;
+            for (int k = qs + 1; k <= qe - 1; ++k) {                    // deletion before query position k
+                const uint32_t rp = bit_range(qs, k), rs = bit_range(k, qe);
+                if ((fM & rp) | (f0 & rs)) continue;
+                const uint32_t mb = (mM & rp) | (m0 & rs);
+                const int mm = __popc(mb);
+                if (mm > c.M || mm + 1 + u > B) continue;
+                const AlnState a{mb, 0u, 1u << k, 0u, mm, 1};
+                if (alignment_problematic(gv, c, strand, a, qs, qe, base - 1 + qs, base + qe, cs, ce)) return true;
+            }
+            for (int k = qs + 1; k <= qe - 2; ++k) {                    // insertion at query position k
+                const uint32_t rp = bit_range(qs, k), rs = bit_range(k + 1, qe);
+                if ((fP & rp) | (f0 & rs)) continue;
+                const uint32_t mb = (mP & rp) | (m0 & rs);
+                const int mm = __popc(mb);
+                if (mm > c.M || mm + 1 + u > B) continue;
+                const AlnState a{mb, 1u << k, 0u, 0u, mm, 1};
+                if (alignment_problematic(gv, c, strand, a, qs, qe, base + 1 + qs, base + qe, cs, ce)) return true;
+            }
+        }
+    }
+    return false;
+}
+
 constexpr int kMaxDepth = MG_MAX_GRNA_LEN + MG_MAX_GAPS + 2;
 
 struct Frame {
@@ -223,6 +307,8 @@ static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const Ge
     if (ci < 0 || gv.cend[ci] <= flo) return false;
     const int64_t cs = strand > 0 ? gv.cstart[ci] : gv.glen - gv.cend[ci];
     const int64_t ce = strand > 0 ? gv.cend[ci] : gv.glen - gv.cstart[ci];
+
+    if (c.n_units == 0 && c.Gp <= 1) return verify_nopattern_one_gap(gv, c, q, strand, e, cs, ce);
 
     Frame st[kMaxDepth];
     for (int qe = L; qe >= 1; --qe) {
@@ -272,6 +358,17 @@ static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const Ge
         }
     }
     return false;
+}
+
+}  // namespace mg
+
+namespace mg {
+
+// Hand a prefilter survivor to the verifier pass.  The counter keeps counting past the capacity: the host sees
+// the overflow, learns the survivor density from it and re-runs the range in slices that fit.
+__device__ __forceinline__ void emit_candidate(const GeneralCtx& c, int q, int64_t e) {
+    const unsigned long long slot = atomicAdd(c.cand_count, 1ull);
+    if (slot < c.cand_cap) c.cand[slot] = Cand{q, 0, e};
 }
 
 }  // namespace mg
