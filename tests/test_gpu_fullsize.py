@@ -1,0 +1,106 @@
+"""Size-independent properties at BASELINE.json's full genome size (one 135 Mb synthetic genome, 5 contigs):
+planted near-matches are found exactly once each, masks remove exactly the masked ones, window shards add up,
+and a gRNA and its reverse complement get the same count.  (The oracle cannot run at this size.)"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GENOME = 135_000_000
+CONTIGS = 5
+L = 20
+
+
+def _rc(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+@pytest.fixture(scope="module")
+def world():
+    import torch
+    from minorg_b200 import _lib
+    _lib.init(0)
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2026)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    ascii_ = torch.take(lut, torch.randint(0, 4, (GENOME,), dtype=torch.uint8, device=dev, generator=gen).to(torch.int64))
+    rng = np.random.Generator(np.random.PCG64(5))
+    grnas = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=L)) for _ in range(64)]
+    clen = GENOME // CONTIGS
+    planted = []          # (gRNA index, contig, start, n_mismatch, strand)
+    for gi, g in enumerate(grnas[:48]):
+        for rep in range(3):
+            mm = rep                      # 0, 1, 2 mismatches
+            seq = list(g)
+            for p in rng.choice(L, size=mm, replace=False):
+                seq[p] = "ACGT"[("ACGT".index(seq[p]) + 1 + int(rng.integers(0, 3))) % 4]
+            seq = "".join(seq)
+            strand = 1 if (gi + rep) % 2 == 0 else -1
+            text = seq if strand == 1 else _rc(seq)
+            c = int(rng.integers(0, CONTIGS))
+            start = int(rng.integers(1000, clen - 1000)) // 64 * 64 + gi      # plants never overlap (64-aligned + gi)
+            if gi < 4 and rep < 2:                                            # a few sit exactly at a contig start / end
+                c, start = gi, (0 if rep == 0 else clen - L)
+            a = c * clen + start
+            ascii_[a:a + L] = torch.from_numpy(np.frombuffer(text.encode(), dtype=np.uint8).copy()).to(dev)
+            planted.append((gi, c, start, mm, strand))
+    offsets = np.arange(CONTIGS + 1, dtype=np.int64) * clen
+    stream = torch.cuda.current_stream().cuda_stream
+    genome = _lib.Genome.from_device_ascii(ascii_.data_ptr(), offsets, ["c%d" % i for i in range(CONTIGS)], stream=stream)
+    torch.cuda.synchronize()
+    del ascii_
+    yield dict(lib=_lib, torch=torch, genome=genome, grnas=grnas, planted=planted, stream=stream)
+    genome.free()
+
+
+def _screen(w, grnas, M, win=(0, -1), masks=None):
+    from minorg_b200.ot_regex import make_criteria
+    torch, L_ = w["torch"], w["lib"]
+    w["genome"].set_masks(masks or [])
+    q = L_.Queries(grnas, stream=w["stream"])
+    counts = torch.zeros(2 * len(grnas), dtype=torch.int32, device="cuda")
+    L_.screen(w["genome"], q, make_criteria(ot_mismatch=M + 1), None, counts.data_ptr(), win_begin=win[0], win_end=win[1],
+              stream=w["stream"])
+    c = counts.cpu().numpy().astype(np.int64)
+    q.free()
+    return c[:len(grnas)] + c[len(grnas):]
+
+
+def test_planted_hits_found(world):
+    for M in (0, 1, 2):
+        want = np.zeros(len(world["grnas"]), dtype=np.int64)
+        for gi, _, _, mm, _ in world["planted"]:
+            want[gi] += mm <= M
+        got = _screen(world, world["grnas"], M)
+        assert (got >= want).all(), M
+        # chance hits over 2 x 135 Mb of random sequence, 64 gRNA: 1 / 61 / 1771 of 4^20 20-mers lie within 0 / 1 / 2
+        # mismatches => expected 0.016 / 1.0 / 28 extra hits in total
+        assert (got - want).sum() <= (1, 6, 60)[M], (M, got - want)
+        if M == 2:
+            assert (got - want).sum() >= 8
+
+
+def test_masks_remove_exactly_the_masked_plants(world):
+    M = 2
+    base = _screen(world, world["grnas"], M)
+    masked = [p for i, p in enumerate(world["planted"]) if i % 3 == 0]
+    got = _screen(world, world["grnas"], M, masks=[(c, s, s + L) for _, c, s, _, _ in masked])
+    drop = np.zeros_like(base)
+    for gi, *_ in masked:
+        drop[gi] += 1
+    assert np.array_equal(base - got, drop)
+    # a mask one base too short on either side does not cover the hit (MINORg.py:1994-2000: span inside ONE interval)
+    got2 = _screen(world, world["grnas"], M, masks=[(c, s + 1, s + L) for _, c, s, _, _ in masked] +
+                   [(c, s, s + L - 1) for _, c, s, _, _ in masked])
+    assert np.array_equal(got2, base)
+
+
+def test_window_shards_add_up_and_strand_symmetry(world):
+    M = 2
+    whole = _screen(world, world["grnas"], M)
+    glen = world["genome"].global_length
+    cuts = [0, glen // 8 + 5, glen // 2, glen // 2 + 1, glen]
+    parts = sum(_screen(world, world["grnas"], M, win=(a, b)) for a, b in zip(cuts[:-1], cuts[1:]))
+    assert np.array_equal(whole, parts)
+    assert np.array_equal(_screen(world, [_rc(g) for g in world["grnas"]], M), whole)
