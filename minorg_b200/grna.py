@@ -15,24 +15,29 @@ def _status_value(v):
 
 
 class CheckObj:
-    """Named tri-state checks: True/False/None <-> pass/fail/NA (grna.py:28-161)."""
+    """Named tri-state checks: True/False/None <-> pass/fail/NA (grna.py:28-161).  The value table is
+    created on first write: a million-hit enumeration should not allocate a million dicts."""
+    _default_checks = ()
+    __slots__ = ("_checks",)
 
-    def __init__(self, *names):
-        self._checks = {n: None for n in names}
+    def __init__(self):
+        self._checks = None
 
     @property
     def check_names(self):
-        return list(self._checks)
+        return list(self._default_checks) + [n for n in (self._checks or ()) if n not in self._default_checks]
 
     def set_check(self, name, status):
+        if self._checks is None:
+            self._checks = {}
         self._checks[name] = _status_value(status)
 
     def check(self, name, mode="bool"):
-        v = self._checks.get(name)
+        v = self._checks.get(name) if self._checks else None
         return _status_text(v) if mode == "str" else v
 
     def check_exists(self, name):
-        return name in self._checks
+        return name in self._default_checks or bool(self._checks and name in self._checks)
 
 
 class Target:
@@ -53,8 +58,11 @@ class Target:
 
 
 class gRNASeq(CheckObj):
+    _default_checks = ("background", "GC")
+    __slots__ = ("_seq", "id")
+
     def __init__(self, seq):
-        super().__init__("background", "GC")
+        self._checks = None
         self._seq = str(seq).upper()
         self.id = None
 
@@ -69,8 +77,11 @@ class gRNASeq(CheckObj):
 class gRNAHit(CheckObj):
     """One occurrence: forward-strand, 0-based, end-exclusive range on its target (grna.py:1144)."""
 
+    _default_checks = ("background", "GC", "feature", "exclude")
+    __slots__ = ("target", "_range", "strand", "hit_id", "_parent_sense")
+
     def __init__(self, target, start, end, strand, hit_id):
-        super().__init__("background", "GC", "feature", "exclude")
+        self._checks = None
         self.target, self._range, self.strand, self.hit_id = target, (start, end), strand, hit_id
         self._parent_sense = None
 
@@ -172,6 +183,38 @@ class gRNAHits:
             if all(v is True or (accept_invalid and v is None) for v in vals):
                 out.append(s.seq)
         return out
+
+    def parse_from_mapping(self, fname, targets=None):
+        """Read a MINORg .map file written by write_mapping (version 5; versions 2-4 are accepted too, they
+        only lack the 'target length' column or call 'set' 'group'; grna.py:447-514).  Restores sequences, hits,
+        ids and check columns so filter/minimumset style steps can resume from files."""
+        seq_targets = {}
+        if targets:
+            from .fasta import fasta_to_dict
+            seq_targets = {k: Target(v, id=k, strand="+") for k, v in fasta_to_dict(targets).items()}
+        with open(fname) as fh:
+            rows = [ln.rstrip("\n").split("\t") for ln in fh if ln.strip()]
+        header, data = rows[0], rows[1:]
+        set_col = header.index("set") if "set" in header else header.index("group")
+        has_len = "target length" in header
+        checks = header[set_col + 1:]
+        dummy = {}
+        for row in data:
+            if has_len:
+                gid, seq, tid, tlen, sense, strand, start, end = row[:8]
+            else:
+                gid, seq, tid, sense, strand, start, end = row[:7]
+                tlen = 0
+            target = seq_targets.get(tid)
+            if target is None:
+                target = dummy.setdefault((tid, tlen), Target("N" * int(tlen), id=tid, strand="+"))
+            hit = gRNAHit(target, int(start) - 1, int(end), strand, gid)
+            hit.set_parent_sense(sense)
+            self.add_hit(seq, hit)
+            gs = self.get_gRNAseq_by_seq(seq)
+            gs.id = gid
+            for name, val in zip(checks, row[set_col + 1:]):
+                (gs if name in ("background", "exclude", "GC") else hit).set_check(name, val)
 
     # -- writers ---------------------------------------------------------------------------------
     def write_fasta(self, fout, ids=(), seqs=(), write_all=False):

@@ -142,3 +142,41 @@ def test_prefilter_bounds_are_sound():
                              for a, n in pieces)
                     assert ok, (pat, gcap, kinds, qs, qe, pieces)
     assert checked > 1000
+
+
+def _hits_from_oracle(entries):
+    from minorg_b200.grna import Target, gRNAHit, gRNAHits
+    h, targets = gRNAHits(), {}
+    for seq, hs in entries:
+        for (tid, a, b, strand, hid, tlen) in hs:
+            t = targets.setdefault((tid, tlen), Target("N" * tlen, id=tid, strand="+"))
+            h.add_hit(seq, gRNAHit(t, a, b, strand, hid))
+    return h
+
+
+def test_grna_writers_match_reference_text(golden, tmp_path):
+    """write_fasta / write_mapping (v5) byte-for-byte against files written by the reference's gRNAHits."""
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    n = 0
+    for r in golden("enumerate.json")["rows"]:
+        if "map_text" not in r:
+            continue
+        h = _hits_from_oracle(O.find_multi_grna(os.path.join(gdir, r["fasta"]), r["pam"], r["L"]))
+        fa, mp = str(tmp_path / "g.fa"), str(tmp_path / "g.map")
+        h.write_fasta(fa, write_all=True)
+        h.write_mapping(mp, write_all=True, write_checks=True)
+        assert open(fa).read() == r["fasta_text"] and open(mp).read() == r["map_text"]
+        # resume: read the .map back, set a check, write again
+        from minorg_b200.grna import gRNAHits
+        back = gRNAHits()
+        back.parse_from_mapping(mp)
+        assert back.seqs == h.seqs and [s.id for s in back.flatten_gRNAseqs()] == [s.id for s in h.flatten_gRNAseqs()]
+        mp2 = str(tmp_path / "g2.map")
+        back.write_mapping(mp2, write_all=True, write_checks=True)
+        assert open(mp2).read() == r["map_text"]
+        back.set_seqs_check("background", False, back.seqs[:1])
+        assert back.get_gRNAseq_by_seq(back.seqs[0]).check("background", mode="str") == "fail"
+        assert back.filter_seqs("background", accept_invalid=True) == back.seqs[1:]
+        n += 1
+    assert n >= 10
