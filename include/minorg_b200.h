@@ -183,7 +183,8 @@ int64_t mg_genome_global_length(const mg_genome* g);
 int mg_last_screen_stats(uint64_t* out /* [2] */);
 
 /* Integer-pipe microbenchmarks used for the roofline denominators of the scan kernel (bench.py):
- * which: 0 = LOP3 (ALU pipe) lane-ops, 1 = shared-memory 32-bit loads (LSU).  Returns Gops/s in *gops. */
+ * which: 0 = LOP3 (ALU pipe) lane-ops, 1 = shared-memory 32-bit loads (LSU), 2 / 3 = 64- / 128-bit shared-memory
+ * loads with the scan's broadcast pattern (4 adjacent entries per warp).  Returns G lane-instructions/s in *gops. */
 int mg_microbench(int which, double* gops, void* stream);
 
 #ifdef __cplusplus

@@ -48,6 +48,35 @@ __global__ void __launch_bounds__(1024, 1) ubench_lds(uint32_t* out, int iters) 
     if (acc == 0x12345u) out[0] = acc;
 }
 
+// Same access pattern as the scan (every lane of a warp reads one of 4 adjacent table entries), with 8- and
+// 16-byte entries: does a broadcast-heavy wide load cost one wavefront or several?
+template <int WORDS>
+__global__ void __launch_bounds__(1024, 1) ubench_lds_wide(uint32_t* out, int iters) {
+    __shared__ __align__(16) uint32_t sm[8192];
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) sm[i] = i * 2654435761u;
+    __syncthreads();
+    uint32_t acc = 0;
+    uint32_t idx = ((threadIdx.x * 7u) & 3u) + 4u * (threadIdx.x >> 5);   // entry index: 4 adjacent entries per warp
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const uint32_t e = (idx + 4u * u) & (8192u / WORDS - 1u);
+            const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sm + e * WORDS);
+            if (WORDS == 2) {
+                uint32_t a, b;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+                acc ^= a ^ b;
+            } else {
+                uint32_t a, b, c, d;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+                acc ^= a ^ b ^ c ^ d;
+            }
+        }
+        idx += 64u;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
 }  // namespace mg
 
 extern "C" {
@@ -61,7 +90,7 @@ int mg_last_screen_stats(uint64_t* out) {
 }
 
 int mg_microbench(int which, double* gops, void* stream) {
-    MG_CHECK_ARG(gops != nullptr && (which == 0 || which == 1));
+    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 3);
     cudaStream_t s = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     MG_CUDA(cudaGetDevice(&dev));
@@ -76,12 +105,14 @@ int mg_microbench(int which, double* gops, void* stream) {
     for (int rep = 0; rep < 4; ++rep) {
         MG_CUDA(cudaEventRecord(e0, s));
         if (which == 0) ubench_lop3<<<sms, 1024, 0, s>>>(d, iters);
-        else ubench_lds<<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 1) ubench_lds<<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 2) ubench_lds_wide<2><<<sms, 1024, 0, s>>>(d, iters);
+        else ubench_lds_wide<4><<<sms, 1024, 0, s>>>(d, iters);
         MG_CUDA(cudaEventRecord(e1, s));
         MG_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
         MG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : 32.0);
+        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : which == 1 ? 32.0 : 16.0);   // load INSTRUCTIONS per lane
         const double r = ops / (ms * 1e-3) / 1e9;
         if (rep > 0 && r > best) best = r;
     }

@@ -15,6 +15,8 @@ namespace mg {
 
 int launch_screen_bitsliced_general(const mg_genome* g, const mg_queries* q, int k, const GeneralCtx* d_ctx,
                                     int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s);
+int launch_gapped_rows(const mg_genome* g, const mg_queries* q, const GeneralCtx* d_ctx, int K, int strand, int64_t eb,
+                       int64_t ee, uint32_t** d_tab5_cache, cudaStream_t s);
 
 // ----------------------------------------------------------------------------------------- Myers <= K
 constexpr int kMyersThreads = 128;     // gRNA per CTA (one per thread; a warp shares the text character)
@@ -230,6 +232,9 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
 
     // prefilter over windows [a, b): queues survivors.  strand -1 anchors of a window [p, p+L) end, in
     // reverse-complement coordinates, at glen - p; so windows [a, b) own e' in [glen - b + 1, glen - a + 1).
+    uint32_t* d_tab5 = nullptr;                                   // tables of the bit-sliced edit-distance kernel
+    const char* gapped_env = getenv("MG_GAPPED_PREFILTER");       // "myers": the one-pattern-per-thread kernel (A/B)
+    const bool use_rows = !(gapped_env && strcmp(gapped_env, "myers") == 0);
     auto prefilter = [&](int64_t a, int64_t b) -> int {
         if (by_pieces) {
             const int S = 4 * L + 1;
@@ -248,7 +253,10 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             const int64_t eb = z == 0 ? a + L : g->glen - b + 1, ee = z == 0 ? b + L : g->glen - a + 1;
             const int64_t n_anchor = ee - eb;
             if (n_anchor <= 0) continue;
-            if (by_myers) {
+            if (by_myers && use_rows) {
+                const int r2 = launch_gapped_rows(g, q, d_ctx, K, strand, eb, ee, &d_tab5, s);
+                if (r2 != MG_OK) return r2;
+            } else if (by_myers) {
                 dim3 grid((unsigned)((n_anchor + kMyersChunk - 1) / kMyersChunk), (unsigned)((q->n + kMyersThreads - 1) / kMyersThreads), 1);
                 myers_kernel<<<grid, kMyersThreads, 0, s>>>(g->view(), q->view(), d_ctx, K, strand, eb, ee, d_counts);
             } else {
@@ -296,7 +304,8 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // d_ctx and the queue must outlive the kernels
     if (getenv("MG_TRACE")) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu\n",
-                                    by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? "myers" : "all-cells", K, total_cand);
+                                    by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? (use_rows ? "edit-rows" : "myers") : "all-cells", K, total_cand);
+    dev_free(d_tab5, s);
     dev_free(h.cand, s);
     dev_free(h.cand_count, s);
     cudaFree(d_ctx);
