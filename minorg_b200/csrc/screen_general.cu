@@ -77,13 +77,15 @@ myers_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, 
 // the scan kernel (OR of the mismatch words of a range == 0).  A gap after (before) the matching range moves
 // the alignment's virtual end by at most Gp, so 2*Gp+1 anchors go to the exact verifier.
 constexpr int kPieceThreads = 512;
+constexpr int kPieceMax = 16;          // positions of a piece that are compared (a longer piece is cut: still necessary)
 
-__global__ void __launch_bounds__(kPieceThreads)
+__global__ void __launch_bounds__(kPieceThreads, 1)
 pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, int groups_per_chunk, int64_t wb,
               int64_t we, uint32_t* __restrict__ counts) {
     extern __shared__ uint32_t tab[];
     const int L = qv.len, S = 4 * L + 1, N = qv.n;
     const int n_pieces = ctx->n_pieces, Gp = ctx->Gp;
+    const int g_split = N / 32;            // groups below hold only '+' queries; group g_split may hold both
     for (int cg = 0; cg < qv.n_groups; cg += groups_per_chunk) {
         const int ng = min(groups_per_chunk, qv.n_groups - cg);
         __syncthreads();
@@ -92,41 +94,45 @@ pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx,
         for (int64_t p = wb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < we; p += (int64_t)gridDim.x * blockDim.x) {
             uint32_t lo, hi, inv;
             load_window(gv, p, lo, hi, inv);
-            uint32_t off[MG_MAX_GRNA_LEN];
+            const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+            for (int op = 0; op < 2 * n_pieces; ++op) {
+                // oriented piece: '+' queries compare gRNA positions [a, a+n), '-' queries the mirrored range
+                const int k = op >> 1;
+                const bool minus = op & 1;
+                const uint32_t m = minus ? ctx->piece_rev[k] : ctx->piece_fwd[k];
+                const int a = __ffs(m) - 1;
+                const int n = min(__popc(m), kPieceMax);
+                uint32_t off[kPieceMax];                   // byte offsets of the table words of this window
 #pragma unroll
-            for (int j = 0; j < MG_MAX_GRNA_LEN; ++j) {
-                const uint32_t code = (j < 16) ? ((lo >> (2 * j)) & 3u) : ((hi >> (2 * (j - 16))) & 3u);
-                off[j] = (j < L) ? ((((inv >> j) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * j) + code)) : (uint32_t)(4 * L);
-            }
-            for (int g = 0; g < ng; ++g) {
-                const uint32_t* t = tab + (size_t)g * S;
-                // a group is entirely '+' queries, entirely '-' (reverse-complement) queries, or straddles N
-                const int q0 = (cg + g) * 32;
-                uint32_t hit = 0u;
-                for (int k = 0; k < n_pieces; ++k) {
-                    const uint32_t mf = ctx->piece_fwd[k], mr = ctx->piece_rev[k];
-                    uint32_t accf = 0u, accr = 0u;
+                for (int x = 0; x < kPieceMax; ++x) {
+                    const int j = min(a + x, L - 1);
+                    const uint32_t code = (uint32_t)(w >> (2 * j)) & 3u;
+                    off[x] = (((inv >> j) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * j) + code) * 4u;
+                }
+                // groups of this orientation inside the resident chunk
+                int g_lo = minus ? max(g_split, cg) : cg;
+                int g_hi = minus ? cg + ng : min(cg + ng, (N + 31) / 32);
+                for (int g = g_lo; g < g_hi; ++g) {
+                    const char* t = reinterpret_cast<const char*>(tab + (size_t)(g - cg) * S);
+                    uint32_t acc = 0u;
 #pragma unroll
-                    for (int j = 0; j < MG_MAX_GRNA_LEN; ++j) {
-                        if (((mf | mr) >> j) & 1u) {
-                            const uint32_t w = t[off[j]];
-                            if ((mf >> j) & 1u) accf |= w;
-                            if ((mr >> j) & 1u) accr |= w;
-                        }
-                    }
-                    // bit i belongs to query q0+i: '+' orientation uses the forward mask, '-' the mirrored one
+                    for (int x = 0; x < kPieceMax; ++x)
+                        if (x < n) acc |= *reinterpret_cast<const uint32_t*>(t + off[x]);
+                    uint32_t hit = ~acc;
+                    if (hit == 0u) continue;
+                    const int q0 = g * 32;
                     uint32_t plus_bits = 0u;
                     if (q0 + 32 <= N) plus_bits = 0xFFFFFFFFu;
                     else if (q0 < N) plus_bits = (1u << (N - q0)) - 1u;
-                    hit |= (~accf & plus_bits) | (~accr & ~plus_bits);
-                }
-                while (hit) {
-                    const int i = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    const int q = q0 + i;
-                    if (q >= 2 * N) continue;
-                    const int64_t e0 = q < N ? p + L : gv.glen - p;
-                    for (int d = -Gp; d <= Gp; ++d) emit_candidate(*ctx, q, e0 + d);
+                    hit &= minus ? ~plus_bits : plus_bits;
+                    while (hit) {
+                        const int i = __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        const int q = q0 + i;
+                        if (q >= 2 * N) continue;
+                        const int64_t e0 = q < N ? p + L : gv.glen - p;
+                        for (int d = -Gp; d <= Gp; ++d) emit_candidate(*ctx, q, e0 + d);
+                    }
                 }
             }
         }

@@ -27,9 +27,9 @@ def main():
         ("ungapped <=4 mm + PAM proximity (.NGG)", 135e6, 10000, 20, dict(ot_mismatch=5, ot_pamless=False), ".NGG"),
         ("ungapped <=4 mm + PAM proximity (TTTV. L=23)", 135e6, 10000, 23, dict(ot_mismatch=5, ot_pamless=False), "TTTV."),
         ("pattern (0mg5,1mg6-)|(0mg6,1m7-) ungapped", 135e6, 10000, 20, dict(ot_pattern="(0mg5,1mg6-)|(0mg6,1m7-)"), ".NGG"),
-        ("gapped <=4 mm / <=1 gap (Myers K=5)", 13.5e6, 1024, 20, dict(ot_mismatch=5, ot_gap=2), ".NGG"),
-        ("gapped <=1 mm / <=1 gap (Myers K=2)", 13.5e6, 1024, 20, dict(ot_mismatch=2, ot_gap=2), ".NGG"),
-        ("pattern 0mg-10,1mg-11- with <=1 gap (config 3)", 13.5e6, 1024, 20, dict(ot_pattern="0mg-10,1mg-11-", ot_gap=2), ".NGG"),
+        ("gapped <=4 mm / <=1 gap (edit distance K=5)", 135e6, 4096, 20, dict(ot_mismatch=5, ot_gap=2), ".NGG"),
+        ("gapped <=1 mm / <=1 gap (edit distance K=2)", 135e6, 4096, 20, dict(ot_mismatch=2, ot_gap=2), ".NGG"),
+        ("pattern 0mg-10,1mg-11- with <=1 gap (config 3)", 135e6, 10000, 20, dict(ot_pattern="0mg-10,1mg-11-", ot_gap=2), ".NGG"),
     ]
     only = sys.argv[1:]
     for name, nb, n, L, kw, pam in cases:
