@@ -277,7 +277,13 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     // Run [wb, we) in slices whose survivors fit the queue; an overflowing slice is re-run in as many parts as
     // its survivor count calls for (nothing of it has been verified yet, so no double counting).
     std::vector<std::pair<int64_t, int64_t>> todo;
-    todo.emplace_back(wb, we);
+    {   // a small probe slice first: its survivor density sizes the remaining slices, so that an overflow (a wasted
+        // prefilter pass) only happens when the density is very uneven
+        const int64_t len = we - wb, probe = len / 64;
+        if (probe >= (1 << 16)) { todo.emplace_back(wb + probe, we); todo.emplace_back(wb, wb + probe); }
+        else todo.emplace_back(wb, we);
+    }
+    bool planned = todo.size() < 2;
     unsigned long long total_cand = 0;
     while (!todo.empty() && rc == MG_OK) {
         const std::pair<int64_t, int64_t> r = todo.back();
@@ -302,6 +308,18 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             continue;
         }
         total_cand += n_cand;
+        if (!planned) {          // just finished the probe: cut the rest into slices of ~cap/3 expected survivors
+            planned = true;
+            const std::pair<int64_t, int64_t> rest = todo.back();
+            todo.pop_back();
+            const double density = (double)n_cand / (double)(r.second - r.first);
+            const double expect = density * (double)(rest.second - rest.first);
+            int64_t parts = (int64_t)(expect / ((double)h.cand_cap / 3.0)) + 1;
+            const int64_t len = rest.second - rest.first;
+            if (parts > len) parts = len;
+            for (int64_t i = parts - 1; i >= 0; --i)
+                todo.emplace_back(rest.first + len * i / parts, rest.first + len * (i + 1) / parts);
+        }
         if (n_cand > 0) {
             verify_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, s>>>(g->view(), q->view(), d_ctx, n_cand, d_counts);
             e = cudaGetLastError();
