@@ -77,6 +77,19 @@ __global__ void __launch_bounds__(1024, 1) ubench_lds_wide(uint32_t* out, int it
     if (acc == 0x12345u) out[0] = acc;
 }
 
+// Indexed constant-bank loads with the scan's pattern (4 distinct adjacent words per warp): a pipe of its own?
+__constant__ uint32_t c_probe[8192];
+__global__ void __launch_bounds__(1024, 1) ubench_ldc(uint32_t* out, int iters) {
+    uint32_t acc = 0;
+    uint32_t idx = ((threadIdx.x * 7u) & 3u) + 4u * (threadIdx.x >> 5);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc ^= c_probe[(idx + 4u * u) & 8191u];
+        idx += 64u;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
 }  // namespace mg
 
 extern "C" {
@@ -90,7 +103,7 @@ int mg_last_screen_stats(uint64_t* out) {
 }
 
 int mg_microbench(int which, double* gops, void* stream) {
-    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 3);
+    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 4);
     cudaStream_t s = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     MG_CUDA(cudaGetDevice(&dev));
@@ -107,7 +120,8 @@ int mg_microbench(int which, double* gops, void* stream) {
         if (which == 0) ubench_lop3<<<sms, 1024, 0, s>>>(d, iters);
         else if (which == 1) ubench_lds<<<sms, 1024, 0, s>>>(d, iters);
         else if (which == 2) ubench_lds_wide<2><<<sms, 1024, 0, s>>>(d, iters);
-        else ubench_lds_wide<4><<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 3) ubench_lds_wide<4><<<sms, 1024, 0, s>>>(d, iters);
+        else ubench_ldc<<<sms, 1024, 0, s>>>(d, iters);
         MG_CUDA(cudaEventRecord(e1, s));
         MG_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
