@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 from . import _lib
-from .fasta import fasta_to_dict, read_fasta, reverse_complement
+from .fasta import fasta_to_dict, read_fasta, read_fasta_arrays, reverse_complement
+from . import distributed as _dist
 from .generate_grna import find_multi_gRNA
 from .ot_regex import MINORgError, OffTargetExpression, make_criteria
 from .pam import PAM
@@ -204,12 +205,23 @@ class MINORg:
 
     # ---- sub-command: filter (background) ------------------------------------------------------
     def _genome(self, fname):
-        """Packed genome of a FASTA file, resident in HBM (cached per file)."""
+        """Packed genome of a FASTA file, resident in HBM (cached per file): (handle, contig names)."""
         fname = _fname(fname)
         if fname not in self._genomes:
-            records = read_fasta(fname)
-            self._genomes[fname] = (_lib.Genome.from_contigs(records), [r[0] for r in records], records)
+            blob, offsets, names = read_fasta_arrays(fname)
+            self._genomes[fname] = (_lib.Genome.from_host_array(blob, offsets, names), names)
         return self._genomes[fname]
+
+    @staticmethod
+    def _ranks():
+        """(rank, world) of the torch.distributed job this process belongs to, (0, 1) outside one."""
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        return 0, 1
 
     def _subject_groups(self):
         ref = {a: _fname(r) for a, r in self.reference.items()}
@@ -229,13 +241,13 @@ class MINORg:
             for fname in group.values():
                 if fname in self.masked:
                     continue
-                genome, names, records = self._genome(fname)
+                genome, names = self._genome(fname)
                 found = set()
                 if plain:
                     for si, ci, start, end, _strand in genome.find_exact([s for _, s in plain]):
                         found.add(Masked(plain[si][0], names[ci], start, end))
                 if other:
-                    found.update(_find_identical_host(other, records))
+                    found.update(_find_identical_host(other, read_fasta(fname)))
                 self.masked[fname] = tuple(found)
 
     def write_mask_report(self, fout):
@@ -258,11 +270,13 @@ class MINORg:
                              ot_unaligned_as_gap=self.ot_unaligned_as_gap, ot_pamless=self.ot_pamless,
                              grna_length=length)
 
-    def offtarget_counts(self, fasta_subject, seqs):
-        """Per-sequence count of problematic, unmasked alignments in one subject file (device screen)."""
+    def offtarget_counts(self, fasta_subject, seqs, windows=None):
+        """Per-sequence count of problematic, unmasked alignments in one subject file (device screen).
+        windows=(rank, world) restricts the scan to that rank's share of the window starts (one genome split
+        over several GPUs; the caller sums the shares, e.g. with distributed.allreduce_counts)."""
         import torch
         fname = _fname(fasta_subject)
-        genome, names, _ = self._genome(fname)
+        genome, names = self._genome(fname)
         index = {n: i for i, n in enumerate(names)}
         genome.set_masks([(index[m.molecule], m.start, m.end) for m in self.masked.get(fname, ()) if m.molecule in index])
         out = np.zeros(len(seqs), dtype=np.int64)
@@ -274,7 +288,9 @@ class MINORg:
             q = _lib.Queries([seqs[i] for i in idx], stream=stream)
             counts = torch.zeros(2 * len(idx), dtype=torch.int32, device="cuda")
             pam = PAM(self.pam, length).program() if not self.ot_pamless else None
-            _lib.screen(genome, q, self._criteria(length), pam, counts.data_ptr(), stream=stream)
+            wb, we = (0, -1) if windows is None else _dist.shard_windows(genome.global_length, length, *windows)
+            if windows is None or we > wb:
+                _lib.screen(genome, q, self._criteria(length), pam, counts.data_ptr(), win_begin=wb, win_end=we, stream=stream)
             c = counts.cpu().numpy().astype(np.int64)
             out[idx] = c[:len(idx)] + c[len(idx):]
             q.free()
@@ -300,27 +316,44 @@ class MINORg:
         print("Masking on-targets")
         self._mask_ontargets(self.target, *([self.ref_gene] if (mask_reference and self.genes and self.ref_gene) else []),
                              *self.mask, *other_mask_fnames)
-        self.write_mask_report(self.results_fname("masked.txt"))
+        if self._ranks()[0] == 0:
+            self.write_mask_report(self.results_fname("masked.txt"))
         print("Finding off-targets")
         ref, query, bg = self._subject_groups()
-        excl, screened = set(), set()
+        files = []
         for enabled, group in (((self.screen_reference or self.query_reference) and ref, ref), (query, query), (bg, bg)):
-            if not enabled:
-                continue
-            for fname in group.values():
-                if fname not in screened:
-                    excl |= self._offtarget_hits(fname)
-            screened |= set(group.values())
+            if enabled:
+                files += [f for f in group.values() if f not in files]      # a file is screened once (:2188)
+        rank, world = self._ranks()
+        if world == 1:
+            excl = set()
+            for fname in files:
+                excl |= self._offtarget_hits(fname)
+        else:
+            # one process per GPU: subject files are dealt to the ranks (a single large genome is split by window
+            # range instead) and the per-gRNA counts are combined with ONE all-reduce over NCCL
+            import torch
+            ids_seqs = list(fasta_to_dict(self.grna_fasta).items())
+            total = np.zeros(len(ids_seqs), dtype=np.int64)
+            if len(files) >= world:
+                for fname in _dist.shard_files(files, rank, world):
+                    total += self.offtarget_counts(fname, [s for _, s in ids_seqs])
+            else:
+                for fname in files:
+                    total += self.offtarget_counts(fname, [s for _, s in ids_seqs], windows=(rank, world))
+            t = torch.from_numpy(total).to("cuda")
+            _dist.allreduce_counts(t)
+            excl = {ids_seqs[i][0] for i in np.nonzero(t.cpu().numpy())[0].tolist()}
         grna_seqs = fasta_to_dict(self.grna_fasta)
         failed = {str(grna_seqs[i]).upper() for i in excl}
         passed = {str(s).upper() for s in grna_seqs.values()} - failed
         self.grna_hits.set_seqs_check("background", True, passed)
         self.grna_hits.set_seqs_check("background", False, failed)
-        if self.auto_update_files:
+        if self.auto_update_files and rank == 0:
             self.write_all_grna_map()
             self.write_pass_grna_files()
 
     def close(self):
-        for g, _, _ in self._genomes.values():
+        for g, _ in self._genomes.values():
             g.free()
         self._genomes = {}

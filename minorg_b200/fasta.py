@@ -51,3 +51,30 @@ def concat_records(records):
         np.cumsum([len(b) for b in bufs], out=offsets[1:])
     blob = np.frombuffer(b"".join(bufs) or b"\0", dtype=np.uint8)
     return blob, offsets, [n for n, _ in records]
+
+
+def read_fasta_arrays(path):
+    """Whole-genome reader for the device path: -> (uint8 array of the concatenated sequence bytes, int64
+    offsets[n+1], names).  Same record semantics as read_fasta (id = first header token, whitespace removed,
+    case preserved) but vectorised with numpy: a 1 Gbp FASTA never becomes a Python str."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw.size == 0:
+        return np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.int64), []
+    line_starts = np.concatenate(([0], np.flatnonzero(raw == 10) + 1))
+    line_starts = line_starts[line_starts < raw.size]
+    header_lines = line_starts[raw[line_starts] == ord(">")]
+    names, pieces, lengths = [], [], []
+    ends = np.concatenate((header_lines[1:], [raw.size]))
+    for h, nxt in zip(header_lines.tolist(), ends.tolist()):
+        eol = h + int(np.argmax(raw[h:nxt] == 10)) if (raw[h:nxt] == 10).any() else nxt
+        fields = raw[h + 1:eol].tobytes().split()
+        names.append(fields[0].decode("latin-1") if fields else "")
+        body = raw[eol:nxt]
+        seq = body[(body != 10) & (body != 13) & (body != 32) & (body != 9)]
+        pieces.append(seq)
+        lengths.append(seq.size)
+    offsets = np.zeros(len(names) + 1, dtype=np.int64)
+    if names:
+        np.cumsum(lengths, out=offsets[1:])
+    blob = np.concatenate(pieces) if pieces and offsets[-1] > 0 else np.zeros(1, dtype=np.uint8)
+    return np.ascontiguousarray(blob), offsets, names
