@@ -18,6 +18,7 @@ from . import _lib
 from .fasta import fasta_to_dict, read_fasta, read_fasta_arrays, reverse_complement
 from . import distributed as _dist
 from .generate_grna import find_multi_gRNA
+from .minimum_set import minimum_sets
 from .ot_regex import MINORgError, OffTargetExpression, make_criteria
 from .pam import PAM
 
@@ -94,6 +95,11 @@ class MINORg:
         self.grna_map = None
         self.pass_fasta = None
         self.pass_map = None
+        self.final_fasta = None
+        self.final_map = None
+        self.sets = 1
+        self.gc_min, self.gc_max = 0.3, 0.7        # parse_config.py:537-540
+        self.exclude = None
         self.masked = {}
         self._genomes = {}
         dev = int(os.environ.get("MINORG_B200_DEVICE", "0")) if device is None else int(device)
@@ -175,7 +181,7 @@ class MINORg:
 
     def valid_grna(self):
         """Sequences whose set sequence-level checks all pass (MINORg.py:1177-1233, sequence checks only)."""
-        names = [n for n in ("background", "GC") if any(s.check(n) is not None for s in self.grna_hits.flatten_gRNAseqs())]
+        names = [n for n in ("background", "GC", "exclude") if any(s.check(n) is not None for s in self.grna_hits.flatten_gRNAseqs())]
         return self.grna_hits.filter_seqs(*names, accept_invalid=self.accept_invalid) if names else self.grna_hits.seqs
 
     def write_pass_grna_files(self, fasta=None, map=None):
@@ -352,6 +358,65 @@ class MINORg:
         if self.auto_update_files and rank == 0:
             self.write_all_grna_map()
             self.write_pass_grna_files()
+
+    # ---- cheap per-sequence filters next to the path ---------------------------
+    def filter_gc(self, gc_min=None, gc_max=None):
+        """Set the 'GC' check: gc_min <= (G+C)/len <= gc_max, '-' ignored (MINORg.py:2222-2238, grna.py:1284-1298,
+        functions.py:490-493)."""
+        lo = self.gc_min if gc_min is None else gc_min
+        hi = self.gc_max if gc_max is None else gc_max
+        for s in self.grna_hits.flatten_gRNAseqs():
+            seq = s.seq.upper().replace("-", "")
+            s.set_check("GC", lo <= (seq.count("G") + seq.count("C")) / len(seq) <= hi)
+        if self.auto_update_files:
+            self.write_all_grna_map()
+            self.write_pass_grna_files()
+
+    def filter_exclude(self):
+        """Set the 'exclude' check from the FASTA file at self.exclude (MINORg.py:2449-2463)."""
+        if self.exclude is not None:
+            banned = {str(v).upper() for v in fasta_to_dict(self.exclude).values()}
+            for s in self.grna_hits.flatten_gRNAseqs():
+                s.set_check("exclude", s.seq not in banned)
+            if self.auto_update_files:
+                self.write_all_grna_map()
+                self.write_pass_grna_files()
+
+    def filter(self, background_check=True, feature_check=False, gc_check=True):
+        """MINORg.py:2465-2486 without the feature check (needs GFF + MAFFT: out of scope)."""
+        if background_check:
+            self.filter_background()
+        if gc_check:
+            self.filter_gc()
+
+    # ---- sub-command: minimumset -----------------------------------------------------------------
+    def minimumset(self, sets=None, manual=None, fasta=None, fout_fasta=None, fout_map=None, fout_eqv=None,
+                   report_full_path=True, **_unused_check_switches):
+        """Generate `sets` mutually exclusive minimum sets of passing gRNA that each cover all targets and write
+        <prefix>_gRNA_final.fasta / .map (MINORg.py:2530-2650, default non-interactive path: LAR set cover,
+        ties -> closest to 5' -> least redundant -> first).  `manual`, `fasta` renaming and the .eqv file are not
+        provided (outside the hot path)."""
+        if not self.grna_hits:
+            raise MINORgError("MINORg.minimumset requires gRNA. You may read a mapping file using"
+                              " self.grna_hits.parse_from_mapping('<path to file>') or use self.grna() to generate gRNA.")
+        sets = self.sets if sets is None else sets
+        targets = {h.target_id for h in self.grna_hits.flatten_hits()}
+        self.filter_exclude()
+        valid = list(self.valid_grna())
+        grna_sets = minimum_sets(self.grna_hits, valid, sets, targets)
+        fout_fasta = fout_fasta or self.final_fasta or self.results_fname("gRNA_final.fasta")
+        fout_map = fout_map or self.final_map or self.results_fname("gRNA_final.map")
+        if grna_sets:
+            self.grna_hits.assign_seqid(assign_all=False)
+            self.grna_hits.write_fasta(fout_fasta, seqs=[s for group in grna_sets for s in group])
+            print("\nFinal gRNA sequence(s) have been written to %s" % (fout_fasta if report_full_path else os.path.basename(fout_fasta)))
+            self.final_fasta = fout_fasta
+            self.grna_hits.write_mapping(fout_map, sets=grna_sets)
+            print("Final gRNA sequence ID(s), gRNA sequence(s), and target(s) have been written to %s"
+                  % (fout_map if report_full_path else os.path.basename(fout_map)))
+            self.final_map = fout_map
+        print("\n%d mutually exclusive gRNA set(s) requested. %d set(s) found." % (sets, len(grna_sets)))
+        return grna_sets
 
     def close(self):
         for g, _ in self._genomes.values():

@@ -58,7 +58,7 @@ class Target:
 
 
 class gRNASeq(CheckObj):
-    _default_checks = ("background", "GC")
+    _default_checks = ("background", "GC", "exclude")
     __slots__ = ("_seq", "id")
 
     def __init__(self, seq):

@@ -474,3 +474,53 @@ if __name__ == "__main__":
         gen_enumerate()
     if "screens" in which:
         gen_screens()
+
+
+# ----------------------------------------------------------------------------- minimum set
+def gen_minimumset():
+    """Runs the reference's default minimum-set path exactly as MINORg.minimumset does (MINORg.py:2571-2626):
+    filter_seqs on 'background', deepcopy, make_get_minimum_set(LAR, tie-break all_best_pos -> all_best_nr)."""
+    import copy
+    import hashlib
+    import tempfile
+    from minorg.minimum_set import make_get_minimum_set, all_best_nr, all_best_pos
+    rows = []
+    srcs = [("synth_targets.fasta", ".NGG", 20), ("sample_CDS.fasta", ".NGG", 20), ("sample_CDS.fasta", "TTTV.", 23),
+            ("config1/targets.fasta", ".NGG", 20), ("sample_CDS.fasta", "ATV.", 20),
+            ("synth_cover.fasta", ".NGG", 20), ("synth_cover.fasta", "TTN", 18), ("synth_cover.fasta", ".NG", 20)]
+    for label, pam, L in srcs:
+        for n_sets in (1, 4):
+            h = quiet(ref_find_multi_gRNA, os.path.join(HERE, label), pam=pam, gRNA_len=L)
+            h.assign_seqid()
+            failed = [s for s in h.seqs if int(hashlib.md5(s.encode()).hexdigest(), 16) % 5 == 0]
+            h.set_seqs_check("background", True, [s for s in h.seqs if s not in failed])
+            h.set_seqs_check("background", False, failed)
+            valid = copy.deepcopy(quiet(h.filter_seqs, "background", accept_invalid=False, accept_invalid_field=True,
+                                        quiet=True, report_invalid_field=True))
+            for_cover = copy.deepcopy(valid)
+            targets = set(hit.target_id for hit in h.flatten_hits())
+            tie = lambda cov, all_cov, covered: tuple(all_best_nr(all_best_pos(cov, all_cov, covered), all_cov, covered).items())[0]
+            get = make_get_minimum_set(for_cover, prioritise_nr=False, manual_check=False, targets=targets,
+                                       tie_breaker=tie, suppress_warning=True)
+            sets, err = [], None
+            try:
+                while len(sets) < n_sets:
+                    s = quiet(get)
+                    if not s:
+                        break
+                    sets.append(sorted(s))
+            except Exception as e:
+                err = type(e).__name__
+            row = dict(fasta=label, pam=pam, L=L, n_sets=n_sets, failed=failed, sets=sets, error=err)
+            if sets and err is None:
+                with tempfile.TemporaryDirectory() as td:
+                    mp = os.path.join(td, "f.map")
+                    quiet(valid.write_mapping, mp, sets=sets, version=5)
+                    row["map_text"] = open(mp).read()
+            rows.append(row)
+            print("  minimumset", label, pam, n_sets, "->", [len(s) for s in sets], err)
+    dump("minimumset.json", dict(rows=rows))
+
+
+if __name__ == "__main__" and "minimumset" in sys.argv[1:]:
+    gen_minimumset()

@@ -72,6 +72,18 @@ def test_config1_grna_and_filter_background(cfg1, tmp_path, ot_mismatch, capsys)
     rep = open(os.path.join(str(tmp_path), "cfg1", "cfg1_masked.txt")).read().splitlines()
     assert rep[0] == "#alias\tfname" and "source\tmolecule\tstart\tend\tmasked" in rep
     assert any(l.split("\t")[:4] == ["TAIR10", "chromA", "13", "4905"] for l in rep)
+    # the steps after the path: GC filter, then mutually exclusive minimum sets of passing gRNA
+    m.filter_gc()
+    gc_ok = {s for s, _ in want if 0.3 <= (s.count("G") + s.count("C")) / 20 <= 0.7}
+    assert {s for s, _ in want if m.grna_hits.get_gRNAseq_by_seq(s).check("GC")} == gc_ok
+    sets = m.minimumset(sets=2)
+    passing = {s for (s, _), fl in zip(want, fail) if not fl} & gc_ok
+    assert len(sets) == 2 and not set(sets[0]) & set(sets[1])
+    for group in sets:
+        assert set(group) <= passing
+        assert {h.target_id for s in group for h in m.grna_hits.get_hits(s)} == {"AT5G45050", "AT5G45060"}
+    final = [l.split("\t") for l in open(m.final_map).read().splitlines()[1:]]
+    assert {r[1] for r in final} == set(sets[0]) | set(sets[1]) and {r[8] for r in final} == {"1", "2"}
     m.close()
 
 

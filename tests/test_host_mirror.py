@@ -180,3 +180,24 @@ def test_grna_writers_match_reference_text(golden, tmp_path):
         assert back.filter_seqs("background", accept_invalid=True) == back.seqs[1:]
         n += 1
     assert n >= 10
+
+
+def test_minimum_sets_match_reference(golden, tmp_path):
+    """Default minimum-set path (LAR + tie-breakers) vs sets chosen by the reference's make_get_minimum_set."""
+    import os
+    from minorg_b200.minimum_set import minimum_sets
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    rows = golden("minimumset.json")["rows"]
+    assert len(rows) >= 16 and any(len(r["sets"][0]) >= 4 for r in rows)
+    for r in rows:
+        assert r["error"] is None
+        h = _hits_from_oracle(O.find_multi_grna(os.path.join(gdir, r["fasta"]), r["pam"], r["L"]))
+        h.assign_seqid()
+        h.set_seqs_check("background", True, [s for s in h.seqs if s not in r["failed"]])
+        h.set_seqs_check("background", False, r["failed"])
+        valid = h.filter_seqs("background")
+        got = minimum_sets(h, valid, r["n_sets"])
+        assert [sorted(s) for s in got] == r["sets"], (r["fasta"], r["pam"], r["n_sets"])
+        mp = str(tmp_path / "final.map")
+        h.write_mapping(mp, sets=got)
+        assert open(mp).read() == r["map_text"]
