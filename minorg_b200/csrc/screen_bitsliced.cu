@@ -84,7 +84,7 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
                         unsigned long long* __restrict__ stats) {
     constexpr int S = 4 * L + 1;                     // table words per group
     constexpr int NB = mgcsa::CountBits<L>::value;
-    constexpr int T1 = SPLIT ? mgcsa::SplitOf<L>::value : 0;      // positions summed before the early-out test
+    constexpr int T1 = SPLIT ? mgcsa::SplitOf<L, K>::value : 0;   // positions summed before the early-out test
     constexpr int NB1 = mgcsa::CountBits<(T1 > 0 ? T1 : 1)>::value;
     extern __shared__ uint32_t tab[];
 
@@ -141,7 +141,7 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
 #pragma unroll
                     for (int j = T1; j < L; ++j) x2[j - T1] = *reinterpret_cast<const uint32_t*>(t + off[j]);
                     uint32_t bits[NB];
-                    mgcsa::csa_count_rest<L>(part, x2, bits);
+                    mgcsa::csa_count_rest<L, T1>(part, x2, bits);
                     hit = (K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr);
                 } else {
                     uint32_t x[L];

@@ -24,6 +24,8 @@ def main():
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
     cases = [
         ("ungapped <=4 mm, PAM-less (fast path)", 135e6, 10000, 20, dict(ot_mismatch=5), ".NGG"),
+        ("reference defaults: ot_mismatch=1 (exact matches), PAM-less", 135e6, 10000, 20, dict(ot_mismatch=1), ".NGG"),
+        ("ungapped <=2 mm, PAM-less", 135e6, 10000, 20, dict(ot_mismatch=3), ".NGG"),
         ("ungapped <=4 mm + PAM proximity (.NGG)", 135e6, 10000, 20, dict(ot_mismatch=5, ot_pamless=False), ".NGG"),
         ("ungapped <=4 mm + PAM proximity (TTTV. L=23)", 135e6, 10000, 23, dict(ot_mismatch=5, ot_pamless=False), "TTTV."),
         ("pattern (0mg5,1mg6-)|(0mg6,1m7-) ungapped", 135e6, 10000, 20, dict(ot_pattern="(0mg5,1mg6-)|(0mg6,1m7-)"), ".NGG"),
