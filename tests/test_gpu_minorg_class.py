@@ -121,3 +121,28 @@ def test_config1_pattern_and_pam_modes(cfg1, tmp_path):
         got = [m.grna_hits.get_gRNAseq_by_seq(s).check("background") is False for s in seqs]
         assert got == want, kw
         m.close()
+
+
+def test_cli_full_then_resume_from_map(cfg1, tmp_path):
+    """`python -m minorg_b200 full ...` and a second `filter` + `minimumset` run resumed from the .map file."""
+    from minorg_b200.__main__ import main
+    out = tmp_path / "cli"
+    common = ["-d", str(out), "--prefix", "run", "-t", str(cfg1 / "targets.fasta")]
+    subj = ["-q", str(cfg1 / "subset_9654.fasta"), "-q", str(cfg1 / "subset_9655.fasta"),
+            "--assembly", str(cfg1 / "subset_ref_TAIR10.fasta"), "--screen-ref", "--ot-mismatch", "2"]
+    assert main(["full"] + common + subj + ["-s", "2"]) == 0
+    all_map = out / "run" / "run_gRNA_all.map"
+    rows = [l.split("\t") for l in open(all_map).read().splitlines()]
+    assert rows[0][-3:] == ["background", "GC", "feature"]
+    want = O.find_multi_grna(str(cfg1 / "targets.fasta"), ".NGG", 20)
+    fail, _ = _oracle_background(cfg1, want, ["subset_ref_TAIR10.fasta", "subset_9654.fasta", "subset_9655.fasta"], 2)
+    bg = {r[1]: r[-3] for r in rows[1:]}
+    assert bg == {s: ("fail" if fl else "pass") for (s, _), fl in zip(want, fail)}
+    final1 = open(out / "run" / "run_gRNA_final.map").read()
+    assert len({l.split("\t")[8] for l in final1.splitlines()[1:]}) == 2
+    # resume: re-screen from the .map with a stricter budget, then pick sets again
+    assert main(["filter", "-m", str(all_map)] + common + subj[:-1] + ["3"]) == 0
+    rows2 = [l.split("\t") for l in open(all_map).read().splitlines()]
+    fail3, _ = _oracle_background(cfg1, want, ["subset_ref_TAIR10.fasta", "subset_9654.fasta", "subset_9655.fasta"], 3)
+    assert {r[1]: r[-3] for r in rows2[1:]} == {s: ("fail" if fl else "pass") for (s, _), fl in zip(want, fail3)}
+    assert main(["minimumset", "-m", str(all_map), "-d", str(out), "--prefix", "run", "-s", "1"]) == 0
