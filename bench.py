@@ -30,8 +30,8 @@ TARGET_LEN = 2000
 GRNA_LEN = 20
 MAX_MISMATCH = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size (8x135 Mb, N=1) scan launch, from the ncu capture
-# summarised in profiles/ (see DESIGN.md); algorithmic bytes are 405 MB genome + 30 MB of query tables (148 CTAs x 202.5 KB)
-NCU_DRAM_BYTES_PER_LAUNCH = 445207296   # profiles/r01_bitsliced_v2_fullsize_ncu_full.tsv: 430.43 MB read + 14.78 MB written
+# summarised in profiles/ (see DESIGN.md); algorithmic bytes are 2 query chunks x 405 MB genome + 34 MB of query tables
+NCU_DRAM_BYTES_PER_LAUNCH = 860234752   # profiles/r01_pairs_v3_fullsize_dram.csv: 843.68 MB read + 16.56 MB written
 
 
 def parse_args():
@@ -368,28 +368,31 @@ def main():
     my_bases = sum(clens) * len(my_genomes)
     cells_per_launch = 2.0 * n * my_bases
     achieved = cells_per_launch / (kern_ms / 1e3) / 1e12
-    t1 = (3 * GRNA_LEN + 3) // 4
+    # pair-word scan (screen_pairs_kernel<20,4>): stage 1 = 10 pair words per lane (shared memory) + 19 LOP3; the
+    # fraction f2 of steps that survives the vote adds the exact count: 20 per-position words (global/L2) + ~60 ALU ops
+    t_pairs = 10
     f2 = (stage2 / steps_cnt) if steps_cnt else 1.0
-    loads_per_step = t1 + f2 * (GRNA_LEN - t1)
-    alu_per_step = 25.0 + f2 * 17.0        # SASS: 22 adder + 2 compare LOP3 + 1 ISETP, then 14 adder + 3 compare
+    loads_per_step = t_pairs + f2 * GRNA_LEN
+    alu_per_step = 19.0 + f2 * 60.0
     peak_lsu = lds * 1e9 * 32.0 / loads_per_step / 1e12
     peak_alu = lop3 * 1e9 * 32.0 / alu_per_step / 1e12
     peak = min(peak_lsu, peak_alu)
     brute = lds * 1e9 * 32.0 / GRNA_LEN / 1e12
-    alg_bytes = my_bases * 0.375          # packed genome (2-bit bases + 1-bit invalid plane) streamed once per launch
+    n_chunks = -(-((2 * n + 31) // 32) // 352)     # 352 query groups of pair tables fit one SM's shared memory
+    alg_bytes = my_bases * 0.375 * n_chunks   # packed genome (2-bit bases + 1-bit invalid plane) streamed once per query chunk
     roofline = {"bound": "lsu(shared-memory loads)" if peak_lsu <= peak_alu else "alu(lop3)", "achieved": achieved,
                 "peak": peak, "unit": "Tcell/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.genome_mb == 135.0 and world == 1) else None,
-                "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, N=1 full-size launch)",
+                "traffic_source": "profiles/r01_pairs_v3_fullsize_dram.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, N=1 full-size launch)",
                 "peak_source": "mg_microbench on this GPU: LOP3 %.0f Glane-op/s, LDS.32 %.0f Glane-op/s" % (lop3, lds),
                 "work_per_step": {"second_stage_fraction": f2, "lds_per_lane": loads_per_step, "alu_per_lane": alu_per_step},
                 "ceilings_tcell_s": {"lsu_shared": peak_lsu, "alu_lop3": peak_alu, "lsu_without_early_out": brute},
                 "frac_of_ceiling_without_early_out": achieved / brute,
-                "kernel": "screen_bitsliced_kernel<20,4,1024>", "kernel_ms": kern_ms,
+                "kernel": "screen_pairs_kernel<20,4,1024>", "kernel_ms": kern_ms,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_gbs": alg_bytes / (kern_ms / 1e3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "peak_source": peaks_src,
-                        "note": "0.375 B/base once per launch: HBM is ~4 orders below its roofline; the scan is integer-pipe bound"}}
+                        "note": "0.375 B/base once per query chunk: HBM is ~3 orders below its roofline; the scan is integer-pipe bound"}}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and harr is not None:

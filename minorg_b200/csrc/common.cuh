@@ -55,6 +55,7 @@ struct GenomeView {
 struct QueriesView {
     const uint8_t* codes;     // [2N][L] base codes 0..3, 4 = invalid; query N+i = revcomp of gRNA i
     const uint32_t* tab;      // [n_groups][4L+1] bit-sliced mismatch words (+ one all-ones word)
+    const uint32_t* tab2;     // [n_groups][16*ceil(L/2)+1] pair words: some base of the position PAIR mismatches
     int n;                    // N
     int len;                  // L
     int n_groups;             // ceil(2N/32)
@@ -128,9 +129,10 @@ struct mg_queries {
     int n = 0, len = 0, n_groups = 0;
     uint8_t* d_codes = nullptr;
     uint32_t* d_tab = nullptr;
+    uint32_t* d_tab2 = nullptr;
     mg::QueriesView view() const {
         mg::QueriesView v;
-        v.codes = d_codes; v.tab = d_tab; v.n = n; v.len = len; v.n_groups = n_groups;
+        v.codes = d_codes; v.tab = d_tab; v.tab2 = d_tab2; v.n = n; v.len = len; v.n_groups = n_groups;
         return v;
     }
 };

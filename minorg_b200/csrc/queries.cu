@@ -48,11 +48,29 @@ __global__ void query_table_kernel(const uint8_t* __restrict__ codes, int nq, in
     tab[idx] = w;
 }
 
+// tab2[g][16k + b0 + 4*b1] bit i = 1 iff query 32g+i mismatches base b0 at position 2k OR base b1 at position 2k+1
+// (a position beyond the gRNA never mismatches); tab2[g][16*NP] = all ones (invalid base in the pair).
+__global__ void query_pair_table_kernel(const uint32_t* __restrict__ tab, int len, int n_groups, uint32_t* __restrict__ tab2) {
+    const int np = (len + 1) / 2, stride = 16 * np + 1, s1 = 4 * len + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_groups * stride) return;
+    const int g = idx / stride, slot = idx % stride;
+    uint32_t w = 0xFFFFFFFFu;
+    if (slot < 16 * np) {
+        const int k = slot >> 4, b0 = slot & 3, b1 = (slot >> 2) & 3;
+        w = tab[(size_t)g * s1 + 4 * (2 * k) + b0];
+        if (2 * k + 1 < len) w |= tab[(size_t)g * s1 + 4 * (2 * k + 1) + b1];
+    }
+    tab2[idx] = w;
+}
+
 int launch_build_queries(const char* d_ascii, mg_queries* q, cudaStream_t s) {
     const int total = 2 * q->n * q->len;
     if (total > 0) query_codes_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_ascii, q->n, q->len, q->d_codes);
     const int words = q->n_groups * (4 * q->len + 1);
     if (words > 0) query_table_kernel<<<(words + 255) / 256, 256, 0, s>>>(q->d_codes, 2 * q->n, q->len, q->n_groups, q->d_tab);
+    const int words2 = q->n_groups * (16 * ((q->len + 1) / 2) + 1);
+    if (words2 > 0) query_pair_table_kernel<<<(words2 + 255) / 256, 256, 0, s>>>(q->d_tab, q->len, q->n_groups, q->d_tab2);
     MG_CUDA(cudaGetLastError());
     return MG_OK;
 }
@@ -74,6 +92,7 @@ int mg_queries_create(const char* grna, int n, int len, void* stream, mg_queries
     MG_CUDA(cudaMalloc(&d_ascii, nbytes + 16));
     MG_CUDA(cudaMalloc(&q->d_codes, 2 * nbytes + 16));
     MG_CUDA(cudaMalloc(&q->d_tab, ((size_t)q->n_groups * (4 * len + 1) + 4) * 4));
+    MG_CUDA(cudaMalloc(&q->d_tab2, ((size_t)q->n_groups * (16 * ((len + 1) / 2) + 1) + 4) * 4));
     if (nbytes) MG_CUDA(cudaMemcpyAsync(d_ascii, grna, nbytes, cudaMemcpyHostToDevice, s));
     int rc = launch_build_queries(d_ascii, q, s);
     cudaStreamSynchronize(s);
@@ -88,7 +107,7 @@ int mg_queries_length(const mg_queries* q) { return q ? q->len : 0; }
 
 void mg_queries_free(mg_queries* q) {
     if (!q) return;
-    cudaFree(q->d_codes); cudaFree(q->d_tab);
+    cudaFree(q->d_codes); cudaFree(q->d_tab); cudaFree(q->d_tab2);
     delete q;
 }
 

@@ -164,6 +164,92 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pair-word variant of the scan (the default): stage 1 looks up, per PAIR of gRNA positions, the word "query i
+// mismatches at least one of the two positions" - one 32-bit load per pair (16 table entries = 16 banks, still
+// conflict-free) instead of one per position.  The number of set pair words never exceeds the number of
+// mismatches, so a cell whose pair count is over budget is decided; on uniform sequence a pair word is set with
+// probability 15/16 and, at L = 20, K = 4, a whole (warp x 32 queries) step survives all 10 pairs only ~1 % of the
+// time.  Survivors take the exact path: L per-position words (from the L2-resident table in global memory) and
+// the full adder tree.  10.2 loads per step instead of 15.5 (single-word early-out) or 20 (plain).
+template <int L, int K, int THREADS, bool GENERAL>
+__global__ void __launch_bounds__(THREADS, 1)
+screen_pairs_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chunk, int64_t wb, int64_t we,
+                    uint32_t* __restrict__ counts, const GeneralCtx* __restrict__ gctx,
+                    unsigned long long* __restrict__ stats) {
+    constexpr int NP = (L + 1) / 2;                  // position pairs (an odd last position pairs with "always matches")
+    constexpr int T = mgcsa::PairSplit<L, K>::value; // pairs tested in stage 1
+    constexpr int S2 = 16 * NP + 1;                  // pair-table words per group in global memory
+    constexpr int SS = 16 * T + 1;                   // ... and in shared memory (only the pairs stage 1 uses)
+    constexpr int S1 = 4 * L + 1;
+    constexpr int NBT = mgcsa::CountBits<T>::value;
+    constexpr int NB = mgcsa::CountBits<L>::value;
+    extern __shared__ uint32_t tab[];
+
+    const int64_t nwin = we - wb;
+    int64_t per = (nwin + gridDim.x - 1) / gridDim.x;
+    per = (per + 31) / 32 * 32;
+    const int64_t w0 = wb + (int64_t)blockIdx.x * per;
+    const int64_t w1 = min(we, w0 + per);
+    unsigned int n_steps = 0, n_stage2 = 0;
+
+    for (int cg = 0; cg < qv.n_groups; cg += groups_per_chunk) {
+        const int ng = min(groups_per_chunk, qv.n_groups - cg);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ng * SS; i += THREADS) {
+            const int g = i / SS, slot = i % SS;
+            tab[i] = __ldg(qv.tab2 + (size_t)(cg + g) * S2 + (slot < 16 * T ? slot : 16 * NP));
+        }
+        __syncthreads();
+
+        for (int64_t pbase = w0; pbase < w1; pbase += THREADS) {
+            const int64_t p = pbase + threadIdx.x;
+            const bool active = p < w1;
+            uint32_t lo = 0, hi = 0, inv = 0xFFFFFFFFu;
+            if (active) load_window(gv, p, lo, hi, inv);
+            uint32_t off[T];                          // byte offsets of this window's pair words
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const uint32_t nib = (k < 8) ? ((lo >> (4 * k)) & 15u) : ((hi >> (4 * (k - 8))) & 15u);
+                const uint32_t bad = (inv >> (2 * k)) & ((2 * k + 1 < L) ? 3u : 1u);
+                off[k] = (bad ? (uint32_t)(16 * T) : (uint32_t)(16 * k) + nib) * 4u;
+            }
+            const char* t = reinterpret_cast<const char*>(tab);
+#pragma unroll 1
+            for (int g = 0; g < ng; ++g, t += SS * 4) {
+                uint32_t x[T];
+#pragma unroll
+                for (int k = 0; k < T; ++k) x[k] = *reinterpret_cast<const uint32_t*>(t + off[k]);
+                uint32_t part[NBT];
+                mgcsa::csa_count<T>(x, part);
+                const uint32_t alive = (K >= 0) ? le_const_impl<NBT>(part, K) : le_runtime<NBT>(part, kthr);
+                ++n_steps;
+                if (!__any_sync(0xFFFFFFFFu, alive != 0u)) continue;
+                ++n_stage2;
+                // exact count for the whole warp (warp-uniform branch): per-position words from global memory
+                const uint32_t* t1 = qv.tab + (size_t)(cg + g) * S1;
+                uint32_t y[L];
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    const uint32_t code = (j < 16) ? ((lo >> (2 * j)) & 3u) : ((hi >> (2 * (j - 16))) & 3u);
+                    y[j] = __ldg(t1 + (((inv >> j) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * j) + code));
+                }
+                uint32_t bits[NB];
+                mgcsa::csa_count<L>(y, bits);
+                const uint32_t hit = ((K >= 0) ? le_const_impl<NB>(bits, K) : le_runtime<NB>(bits, kthr)) & alive;
+                if (hit) {
+                    if (GENERAL) verify_hits(gv, qv, gctx, hit, cg + g, p);
+                    else report_hits(gv, 2 * qv.n, L, hit, cg + g, p, counts);
+                }
+            }
+        }
+    }
+    if (stats != nullptr && (threadIdx.x & 31) == 0) {
+        atomicAdd(stats, (unsigned long long)n_steps);
+        atomicAdd(stats + 1, (unsigned long long)n_stage2);
+    }
+}
+
 // [0] (warp, query-group) steps, [1] steps that needed the second stage - of the most recent launch
 static unsigned long long* g_stats = nullptr;
 
@@ -178,7 +264,9 @@ template <int L, int K, bool GENERAL = false>
 static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t wb, int64_t we, uint32_t* d_counts,
                       cudaStream_t s, const GeneralCtx* gctx = nullptr) {
     constexpr int THREADS = 1024;
-    constexpr int S = 4 * L + 1;
+    const char* scan_env = getenv("MG_SCAN");            // "singles": the per-position early-out scan (A/B)
+    const bool pairs = L >= 8 && !(scan_env && strcmp(scan_env, "singles") == 0);
+    const int S = pairs ? 16 * mgcsa::PairSplit<L, K>::value + 1 : 4 * L + 1;
     int dev = 0, sms = 0, smem_max = 0;
     MG_CUDA(cudaGetDevice(&dev));
     MG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -186,7 +274,7 @@ static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t
     const int max_groups = (smem_max - 1024) / (S * 4);
     const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
     const size_t smem = (size_t)gpc * S * 4;
-    auto kern = screen_bitsliced_kernel<L, K, THREADS, GENERAL, true>;
+    auto kern = pairs ? screen_pairs_kernel<L, K, THREADS, GENERAL> : screen_bitsliced_kernel<L, K, THREADS, GENERAL, true>;
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nwin = we - wb;
     int64_t grid = (nwin + THREADS - 1) / THREADS;
