@@ -368,12 +368,12 @@ def main():
     my_bases = sum(clens) * len(my_genomes)
     cells_per_launch = 2.0 * n * my_bases
     achieved = cells_per_launch / (kern_ms / 1e3) / 1e12
-    # pair-word scan (screen_pairs_kernel<20,4>): stage 1 = 10 pair words per lane (shared memory) + 19 LOP3; the
+    # pair-word scan (screen_pairs_kernel<20,4>): stage 1 = 10 pair words per lane (shared memory) + 15 LOP3 (SASS); the
     # fraction f2 of steps that survives the vote adds the exact count: 20 per-position words (global/L2) + ~60 ALU ops
     t_pairs = 10
     f2 = (stage2 / steps_cnt) if steps_cnt else 1.0
     loads_per_step = t_pairs + f2 * GRNA_LEN
-    alu_per_step = 19.0 + f2 * 60.0
+    alu_per_step = 15.0 + f2 * 60.0
     peak_lsu = lds * 1e9 * 32.0 / loads_per_step / 1e12
     peak_alu = lop3 * 1e9 * 32.0 / alu_per_step / 1e12
     peak = min(peak_lsu, peak_alu)
