@@ -206,7 +206,7 @@ def test_general_golden_cases(L, golden, capsys):
     assert n >= 30
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(16))
 def test_general_random_vs_python_oracle(L, seed):
     rng = random.Random(100 + seed)
     glen = rng.choice([10, 12])
@@ -232,3 +232,22 @@ def test_general_random_vs_python_oracle(L, seed):
     want, _ = O.screen_exhaustive(grnas, contigs, masks, crit)
     got = _general_via_abi(L, contigs, [(0, 2, 2 + glen + 3)], grnas, k, glen)
     assert [x > 0 for x in got.tolist()] == want, (k, grnas, contigs)
+
+
+def test_three_hundred_thousand_queries(L):
+    """Many query chunks (300 000 gRNA = 18 750 groups) against a small genome, every budget class of the scan."""
+    rng = random.Random(21)
+    contigs = [("x", _random_contig(rng, 6000, "ACGT" * 10 + "N")), ("y", _random_contig(rng, 4000))]
+    grnas = [_random_contig(rng, 20) for _ in range(300000)]
+    for i in range(0, 300000, 97):
+        cid, seq = contigs[i % 2]
+        p = rng.randrange(0, len(seq) - 20)
+        g = list(seq[p:p + 20].replace("N", "G"))
+        for _ in range(i % 4):
+            g[rng.randrange(20)] = rng.choice("ACGT")
+        grnas[i] = "".join(g)
+    for M in (0, 3):
+        got = _hamming_via_abi(L, contigs, [(0, 100, 300)], grnas, M)
+        want = c_oracle.screen_hamming(contigs, [(0, 100, 300)], grnas, M, threads=16)
+        assert np.array_equal(got, want), M
+        assert (got > 0).sum() > 300
