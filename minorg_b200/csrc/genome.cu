@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 
+extern "C" void mg_genome_free(mg_genome* g);
+
 namespace mg {
 
 static thread_local std::string g_err;
@@ -101,12 +103,16 @@ int launch_pack(const char* d_ascii, const std::vector<int64_t>& offsets, mg_gen
 static int genome_alloc(const int64_t* offsets, int n_contigs, cudaStream_t s, mg_genome** out) {
     MG_CHECK_ARG(offsets != nullptr && n_contigs >= 0 && out != nullptr);
     mg_genome* g = new mg_genome();
+    struct Guard {               // frees the half-built handle on every early return below
+        mg_genome*& g; bool armed = true;
+        ~Guard() { if (armed) { mg_genome_free(g); g = nullptr; } }
+    } guard{g};
     MG_CUDA(cudaGetDevice(&g->device));
     g->n_contigs = n_contigs;
     int64_t pos = kPad;
     for (int c = 0; c < n_contigs; ++c) {
         const int64_t n = offsets[c + 1] - offsets[c];
-        if (n < 0) { delete g; set_error("contig %d has negative length", c); return MG_ERR_ARG; }
+        if (n < 0) { set_error("contig %d has negative length", c); return MG_ERR_ARG; }
         pos = (pos + kAlign - 1) / kAlign * kAlign;
         g->clen.push_back(n);
         g->cstart.push_back(pos);
@@ -126,6 +132,7 @@ static int genome_alloc(const int64_t* offsets, int n_contigs, cudaStream_t s, m
         MG_CUDA(cudaMemcpy(g->d_cstart, g->cstart.data(), sizeof(int64_t) * n_contigs, cudaMemcpyHostToDevice));
         MG_CUDA(cudaMemcpy(g->d_cend, g->cend.data(), sizeof(int64_t) * n_contigs, cudaMemcpyHostToDevice));
     }
+    guard.armed = false;
     *out = g;
     return MG_OK;
 }

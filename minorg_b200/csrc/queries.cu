@@ -81,23 +81,29 @@ using namespace mg;
 
 extern "C" {
 
+void mg_queries_free(mg_queries* q);
+
 int mg_queries_create(const char* grna, int n, int len, void* stream, mg_queries** out) {
     MG_CHECK_ARG(out != nullptr && n >= 0 && len >= 1 && len <= MG_MAX_GRNA_LEN && (n == 0 || grna != nullptr));
     MG_CHECK_ARG((int64_t)n * 2 * len < (int64_t)1 << 31);
     cudaStream_t s = (cudaStream_t)stream;
     mg_queries* q = new mg_queries();
+    char* d_ascii = nullptr;
+    struct Guard {               // frees the half-built handle and the staging buffer on every early return below
+        mg_queries*& q; char*& a; bool armed = true;
+        ~Guard() { cudaFree(a); if (armed) { mg_queries_free(q); q = nullptr; } }
+    } guard{q, d_ascii};
     q->n = n; q->len = len; q->n_groups = (2 * n + 31) / 32;
     const size_t nbytes = (size_t)n * len;
-    char* d_ascii = nullptr;
     MG_CUDA(cudaMalloc(&d_ascii, nbytes + 16));
     MG_CUDA(cudaMalloc(&q->d_codes, 2 * nbytes + 16));
     MG_CUDA(cudaMalloc(&q->d_tab, ((size_t)q->n_groups * (4 * len + 1) + 4) * 4));
     MG_CUDA(cudaMalloc(&q->d_tab2, ((size_t)q->n_groups * (16 * ((len + 1) / 2) + 1) + 4) * 4));
     if (nbytes) MG_CUDA(cudaMemcpyAsync(d_ascii, grna, nbytes, cudaMemcpyHostToDevice, s));
     int rc = launch_build_queries(d_ascii, q, s);
-    cudaStreamSynchronize(s);
-    cudaFree(d_ascii);
-    if (rc) { mg_queries_free(q); return rc; }
+    MG_CUDA(cudaStreamSynchronize(s));
+    if (rc) return rc;
+    guard.armed = false;
     *out = q;
     return MG_OK;
 }
