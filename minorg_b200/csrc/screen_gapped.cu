@@ -31,12 +31,28 @@ __device__ __forceinline__ uint32_t lop3_a_or_nor(uint32_t a, uint32_t b, uint32
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xF1;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
 
-// Strand-aware sequential reader of base codes (0..3, 4 = invalid): position pos of the strand's text.
+// Strand-aware sequential reader of base codes (0..3, 4 = invalid): position pos of the strand's text.  Keeps
+// the current 16-base word (and its invalid bits) in registers, so a character costs a few ALU ops, not two loads.
 struct TextReader {
     const GenomeView& gv;
     int strand;
-    __device__ TextReader(const GenomeView& g, int s) : gv(g), strand(s) {}
-    __device__ __forceinline__ int at(int64_t pos) const { return tbase(gv, strand, pos); }
+    int64_t blk;
+    uint32_t word, inv16;
+    __device__ TextReader(const GenomeView& g, int s) : gv(g), strand(s), blk(-2), word(0u), inv16(0xFFFFu) {}
+    __device__ __forceinline__ int at(int64_t pos) {
+        const int64_t f = strand > 0 ? pos : gv.glen - 1 - pos;           // forward-genome coordinate
+        if (f < 0 || f >= gv.glen) return kCodeInvalid;
+        const int64_t b = f >> 4;
+        if (b != blk) {
+            blk = b;
+            word = __ldg(gv.bases + b);
+            inv16 = (__ldg(gv.invalid + (b >> 1)) >> ((unsigned)(b & 1) * 16u)) & 0xFFFFu;
+        }
+        const unsigned k = (unsigned)(f & 15);
+        if ((inv16 >> k) & 1u) return kCodeInvalid;
+        const int c = (int)((word >> (2u * k)) & 3u);
+        return strand > 0 ? c : 3 - c;
+    }
 };
 
 template <int L>
@@ -52,7 +68,7 @@ gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ t
     const int64_t p_first = eb - 1 + ((int64_t)blockIdx.x * kRowsThreads + threadIdx.x) * run;
     const int64_t p_last = min(ee - 1, p_first + run);
     const bool active = p_first < p_last;
-    const TextReader text(gv, strand);
+    TextReader text(gv, strand);
     // score counter bias: c = score + 2^(NB-1) - K - 1, so score <= K  <=>  top bit of c is clear
     const uint32_t init = (uint32_t)(L + (1 << (NB - 1)) - K - 1);
 
