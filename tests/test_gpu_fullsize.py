@@ -104,3 +104,62 @@ def test_window_shards_add_up_and_strand_symmetry(world):
     parts = sum(_screen(world, world["grnas"], M, win=(a, b)) for a, b in zip(cuts[:-1], cuts[1:]))
     assert np.array_equal(whole, parts)
     assert np.array_equal(_screen(world, [_rc(g) for g in world["grnas"]], M), whole)
+
+
+def test_human_scale_genome_beyond_2_31(tmp_path):
+    """BASELINE configs[4] shape: one 3.1 Gbp genome (24 contigs).  Global coordinates exceed 2^31, so every position
+    computation on the path must be 64-bit: hits planted near the END of the genome are found, in every window
+    shard of an 8-way split, and masks near the end apply."""
+    import torch
+    from minorg_b200 import _lib
+    from minorg_b200.distributed import shard_windows
+    from minorg_b200.ot_regex import make_criteria
+    _lib.init(0)
+    dev = torch.device("cuda", 0)
+    total, n_contigs = 3_100_000_000, 24
+    clen = total // n_contigs
+    total = clen * n_contigs
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(30)
+    codes = torch.randint(0, 4, (total,), dtype=torch.uint8, device=dev, generator=gen)
+    codes += 65                                  # 'A'..'D'
+    codes[codes == 66] = ord("C")
+    codes[codes == 68] = ord("T")
+    codes[codes == 67 + 0] = ord("C")
+    ascii_ = codes                               # A, C, C, T mix is fine: any fixed i.i.d. text works here
+    rng = np.random.Generator(np.random.PCG64(31))
+    grnas = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=L)) for _ in range(256)]
+    grnas = [g.replace("G", "A") for g in grnas]                      # text has no G: keep the gRNA alphabet matched
+    plants = []
+    for gi in range(64):
+        c = n_contigs - 1 - (gi % 3)                                   # last contigs: global position > 2.7e9
+        start = clen - 5000 - 100 * gi
+        text = grnas[gi] if gi % 2 == 0 else _rc(grnas[gi])
+        a = c * clen + start
+        ascii_[a:a + L] = torch.from_numpy(np.frombuffer(text.encode(), dtype=np.uint8).copy()).to(dev)
+        plants.append((gi, c, start))
+    offsets = np.arange(n_contigs + 1, dtype=np.int64) * clen
+    stream = torch.cuda.current_stream().cuda_stream
+    genome = _lib.Genome.from_device_ascii(ascii_.data_ptr(), offsets, ["chr%d" % i for i in range(n_contigs)], stream=stream)
+    torch.cuda.synchronize()
+    del ascii_, codes
+    assert genome.global_length > 2 ** 31 and genome.total_bases == total
+    assert genome.decode(n_contigs - 1, clen - 5000, clen - 5000 + L) == grnas[0]
+    q = _lib.Queries(grnas, stream=stream)
+    crit = make_criteria(ot_mismatch=1)
+    n = len(grnas)
+
+    def run(win=(0, -1)):
+        counts = torch.zeros(2 * n, dtype=torch.int32, device="cuda")
+        _lib.screen(genome, q, crit, None, counts.data_ptr(), win_begin=win[0], win_end=win[1], stream=stream)
+        c = counts.cpu().numpy().astype(np.int64)
+        return c[:n] + c[n:]
+    whole = run()
+    assert (whole[:64] >= 1).all()
+    parts = sum(run(shard_windows(genome.global_length, L, r, 8)) for r in range(8))
+    assert np.array_equal(parts, whole)
+    genome.set_masks([(c, s, s + L) for gi, c, s in plants[:32]])
+    masked = run()
+    assert np.array_equal(whole[:32] - masked[:32], np.ones(32, dtype=np.int64)) and np.array_equal(whole[32:], masked[32:])
+    q.free()
+    genome.free()
