@@ -174,6 +174,10 @@ class MINORg:
         self.grna_fasta = fout
         self.grna_hits.write_fasta(fout, write_all=True)
 
+    def write_all_grna_eqv(self, fout=None):
+        self.grna_eqv = fout or self.results_fname("gRNA_all.eqv")
+        self.grna_hits.write_equivalents(self.grna_eqv, write_all=True)
+
     def write_all_grna_map(self, fout=None, write_checks=True):
         fout = fout or self.grna_map or self.results_fname("gRNA_all.map")
         self.grna_map = fout
@@ -191,6 +195,7 @@ class MINORg:
         if seqs:
             self.grna_hits.write_mapping(self.pass_map, sets=[seqs], write_checks=False)
             self.grna_hits.write_fasta(self.pass_fasta, seqs=seqs)
+            self.grna_hits.write_equivalents(self.results_fname("gRNA_pass.eqv"), seqs=seqs)
         else:
             open(self.pass_map, "w").close()
             open(self.pass_fasta, "w").close()
@@ -208,6 +213,7 @@ class MINORg:
         self.write_all_grna_fasta()
         if self.auto_update_files:
             self.write_all_grna_map()
+            self.write_all_grna_eqv()
 
     # ---- sub-command: filter (background) ------------------------------------------------------
     def _genome(self, fname):

@@ -184,6 +184,44 @@ class gRNAHits:
                 out.append(s.seq)
         return out
 
+    def collapse(self, ids=(), seqs=()):
+        """Group gRNA by identical target coverage (grna.py:892-921): -> [(group name, sorted target ids, [gRNASeq])],
+        groups ordered by (-coverage, target ids) and named cg_1.. (zero-padded to the number of groups)."""
+        if seqs:
+            chosen = [self.get_gRNAseq_by_seq(s) for s in seqs]
+        elif ids:
+            chosen = [self.get_gRNAseq_by_id(i) for i in ids]
+        else:
+            chosen = self.flatten_gRNAseqs()
+        groups = {}
+        for gs in chosen:
+            if gs is None:
+                continue
+            cov = tuple(sorted({h.target_id for h in self.get_hits(gs.seq)}))
+            groups.setdefault(cov, []).append(gs)
+        ordered = sorted(groups.items(), key=lambda kv: (-len(kv[0]), kv[0]))
+        width = len(str(len(ordered)))
+        return [("cg_" + str(i + 1).zfill(width), cov, members) for i, (cov, members) in enumerate(ordered)]
+
+    def relative_5prime_pos(self, seq):
+        """Mean distance of the gRNA's hits from the 5' end of their targets (minimum_set.py:101-118)."""
+        hits = self.get_hits(seq)
+        return sum((h.range[0] if h.target.sense != "-" else h.target_len - h.range[1]) for h in hits) / len(hits)
+
+    def write_equivalents(self, fout, ids=(), seqs=(), write_all=False):
+        """.eqv file: gRNA grouped by equivalent coverage (grna.py:1090-1118, minimum_set.py:224-245).  Groups by
+        descending coverage, members by relative position.  (The reference iterates a hash-ordered set here, so
+        its order among groups of equal coverage changes from run to run; ours breaks those ties by group name.)"""
+        if not ids and not seqs and not write_all:
+            open(fout, "w").close()
+            return
+        self.assign_seqid(assign_all=False)
+        with open(fout, "w") as fh:
+            fh.write("\t".join(["coverage group", "coverage", "gRNA id", "gRNA sequence", "relative pos"]) + "\n")
+            for name, cov, members in self.collapse(ids=ids, seqs=seqs):
+                for gs in sorted(members, key=lambda g: (self.relative_5prime_pos(g.seq), g.id)):
+                    fh.write("\t".join([name, str(len(cov)), gs.id, gs.seq, str(round(self.relative_5prime_pos(gs.seq), 2))]) + "\n")
+
     def parse_from_mapping(self, fname, targets=None):
         """Read a MINORg .map file written by write_mapping (version 5; versions 2-4 are accepted too, they
         only lack the 'target length' column or call 'set' 'group'; grna.py:447-514).  Restores sequences, hits,

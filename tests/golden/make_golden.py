@@ -524,3 +524,21 @@ def gen_minimumset():
 
 if __name__ == "__main__" and "minimumset" in sys.argv[1:]:
     gen_minimumset()
+
+
+def gen_eqv():
+    """gRNAHits.write_equivalents (grna.py:1090-1118, minimum_set.py:224-245) on a few enumerations."""
+    import tempfile
+    rows = []
+    for label, pam, L in [("synth_cover.fasta", ".NGG", 20), ("synth_cover.fasta", "TTN", 18), ("sample_CDS.fasta", "TTTV.", 23),
+                          ("config1/targets.fasta", ".NGG", 20), ("synth_targets.fasta", ".NGG", 20)]:
+        h = quiet(ref_find_multi_gRNA, os.path.join(HERE, label), pam=pam, gRNA_len=L)
+        with tempfile.TemporaryDirectory() as td:
+            fo = os.path.join(td, "g.eqv")
+            quiet(h.write_equivalents, fo, write_all=True)
+            rows.append(dict(fasta=label, pam=pam, L=L, eqv_text=open(fo).read()))
+    dump("eqv.json", dict(rows=rows))
+
+
+if __name__ == "__main__" and "eqv" in sys.argv[1:]:
+    gen_eqv()

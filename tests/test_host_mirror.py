@@ -201,3 +201,28 @@ def test_minimum_sets_match_reference(golden, tmp_path):
         mp = str(tmp_path / "final.map")
         h.write_mapping(mp, sets=got)
         assert open(mp).read() == r["map_text"]
+
+
+def test_eqv_matches_reference_up_to_its_hash_order(golden, tmp_path):
+    """.eqv rows, group names and memberships equal the reference's; group order is by descending coverage (the
+    reference's order among equal-coverage groups depends on PYTHONHASHSEED, see grna.write_equivalents)."""
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for r in golden("eqv.json")["rows"]:
+        h = _hits_from_oracle(O.find_multi_grna(os.path.join(gdir, r["fasta"]), r["pam"], r["L"]))
+        fo = str(tmp_path / "g.eqv")
+        h.write_equivalents(fo, write_all=True)
+        got, want = open(fo).read().splitlines(), r["eqv_text"].splitlines()
+        assert got[0] == want[0] and sorted(got[1:]) == sorted(want[1:]), (r["fasta"], r["pam"])
+        cov = [int(l.split("\t")[1]) for l in got[1:]]
+        assert cov == sorted(cov, reverse=True)
+        for lines in (got, want):          # members of a group are contiguous and ordered by relative position
+            seen = []
+            for l in lines[1:]:
+                f = l.split("\t")
+                if not seen or seen[-1][0] != f[0]:
+                    assert f[0] not in [x[0] for x in seen]
+                    seen.append((f[0], float(f[4])))
+                else:
+                    assert float(f[4]) >= seen[-1][1]
+                    seen[-1] = (f[0], float(f[4]))
