@@ -286,6 +286,74 @@ screen_pairs_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chun
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Comparison kernel (MG_SCAN=popc): the per-cell XOR/POPC formulation BASELINE.json's north star starts from - one
+// thread per window, every query compared with  x = w ^ q;  d = (x | x >> 1) & 0x5555...;  mm = popc(d).  Same
+// results as the bit-sliced scan (tests run both); kept to put a measured number next to the design choice:
+// ~12 integer instructions and two quarter-rate POPCs per cell against ~0.8 lane-instructions for the pair scan.
+__global__ void __launch_bounds__(1024, 1)
+screen_popc_kernel(GenomeView gv, QueriesView qv, const uint2* __restrict__ qbits, const uint2* __restrict__ qinv, int K,
+                   int queries_per_chunk, int64_t wb, int64_t we, uint32_t* __restrict__ counts) {
+    extern __shared__ uint2 sq[];                 // [chunk] packed query, then [chunk] its invalid-position mask
+    const int L = qv.len, nq = 2 * qv.n;
+    const unsigned long long even = 0x5555555555555555ull;
+    const unsigned long long lmask = L >= 32 ? even : (((1ull << (2 * L)) - 1ull) & even);
+    for (int c0 = 0; c0 < nq; c0 += queries_per_chunk) {
+        const int m = min(queries_per_chunk, nq - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) { sq[i] = qbits[c0 + i]; sq[queries_per_chunk + i] = qinv[c0 + i]; }
+        __syncthreads();
+        for (int64_t p = wb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < we; p += (int64_t)gridDim.x * blockDim.x) {
+            uint32_t lo, hi, inv;
+            load_window(gv, p, lo, hi, inv);
+            const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+            unsigned long long winv = 0;          // invalid window positions spread to the even bits
+            for (int j = 0; j < L; ++j) winv |= (unsigned long long)((inv >> j) & 1u) << (2 * j);
+            for (int i = 0; i < m; ++i) {
+                const uint2 qb = sq[i], qi = sq[queries_per_chunk + i];
+                const unsigned long long q = ((unsigned long long)qb.y << 32) | qb.x;
+                const unsigned long long x = w ^ q;
+                const unsigned long long d = ((x | (x >> 1)) & lmask) | winv | (((unsigned long long)qi.y << 32) | qi.x);
+                if (__popcll(d) <= K) report_hits(gv, nq, L, 1u << ((c0 + i) & 31), (c0 + i) >> 5, p, counts);
+            }
+        }
+    }
+}
+
+// packs query codes into 2-bit words + invalid masks for the comparison kernel
+__global__ void popc_pack_kernel(const uint8_t* __restrict__ codes, int nq, int len, uint2* __restrict__ qbits, uint2* __restrict__ qinv) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long b = 0, iv = 0;
+    for (int j = 0; j < len; ++j) {
+        const int c = codes[(size_t)q * len + j];
+        if (c >= 4) iv |= 1ull << (2 * j); else b |= (unsigned long long)c << (2 * j);
+    }
+    qbits[q] = make_uint2((uint32_t)b, (uint32_t)(b >> 32));
+    qinv[q] = make_uint2((uint32_t)iv, (uint32_t)(iv >> 32));
+}
+
+static int launch_popc(const mg_genome* g, const mg_queries* q, int k, int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s) {
+    const int nq = 2 * q->n;
+    uint2 *d_b = nullptr, *d_i = nullptr;
+    MG_CUDA(dev_alloc((void**)&d_b, sizeof(uint2) * (size_t)nq, s));
+    MG_CUDA(dev_alloc((void**)&d_i, sizeof(uint2) * (size_t)nq, s));
+    popc_pack_kernel<<<(nq + 255) / 256, 256, 0, s>>>(q->d_codes, nq, q->len, d_b, d_i);
+    int dev = 0, sms = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    MG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int per_chunk = nq < 12288 ? nq : 12288;                         // 16 B per query in shared memory
+    const size_t smem = (size_t)per_chunk * 16;
+    MG_CUDA(cudaFuncSetAttribute(screen_popc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (we - wb + 1023) / 1024;
+    if (grid > sms) grid = sms;
+    screen_popc_kernel<<<(unsigned)grid, 1024, smem, s>>>(g->view(), q->view(), d_b, d_i, k, per_chunk, wb, we, d_counts);
+    MG_CUDA(cudaGetLastError());
+    dev_free(d_b, s);
+    dev_free(d_i, s);
+    return MG_OK;
+}
+
 // [0] (warp, query-group) steps, [1] steps that needed the second stage - of the most recent launch
 static unsigned long long* g_stats = nullptr;
 
@@ -340,6 +408,10 @@ int launch_screen_bitsliced(const mg_genome* g, const mg_queries* q, int max_mis
                             uint32_t* d_counts, cudaStream_t s) {
     if (q->n == 0 || we <= wb) return MG_OK;
     const int k = max_mismatch;
+    {
+        const char* scan_env = getenv("MG_SCAN");
+        if (scan_env && strcmp(scan_env, "popc") == 0) return launch_popc(g, q, k, wb, we, d_counts, s);
+    }
     switch (q->len) {
 #define MG_CASE_FULL(LL) case LL: return dispatch_k<LL>(g, q, k, wb, we, d_counts, s);
 #define MG_CASE_RT(LL) case LL: return launch_one<LL, -1>(g, q, k, wb, we, d_counts, s);
