@@ -90,6 +90,32 @@ __global__ void __launch_bounds__(1024, 1) ubench_ldc(uint32_t* out, int iters) 
     if (acc == 0x12345u) out[0] = acc;
 }
 
+// Warp shuffles as a lookup path: alone (MIX = 0) and interleaved 1:1 with shared-memory loads (MIX = 1) - do the two
+// share one pipe?
+template <int MIX>
+__global__ void __launch_bounds__(1024, 1) ubench_shfl(uint32_t* out, int iters) {
+    __shared__ uint32_t sm[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i * 2654435761u;
+    __syncthreads();
+    uint32_t acc = 0, v = threadIdx.x * 40503u;
+    uint32_t idx = (threadIdx.x & 3u) + 4u * (threadIdx.x >> 5);
+    int src = (threadIdx.x * 7) & 31;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            acc ^= __shfl_sync(0xFFFFFFFFu, v + u, (src + u) & 31);
+            if (MIX) {
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((uint32_t)__cvta_generic_to_shared(sm + ((idx + 4u * u) & 4095u))));
+                acc ^= w;
+            }
+        }
+        idx += 64u;
+        v += acc;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
 }  // namespace mg
 
 extern "C" {
@@ -103,7 +129,7 @@ int mg_last_screen_stats(uint64_t* out) {
 }
 
 int mg_microbench(int which, double* gops, void* stream) {
-    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 4);
+    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 6);
     cudaStream_t s = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     MG_CUDA(cudaGetDevice(&dev));
@@ -121,12 +147,14 @@ int mg_microbench(int which, double* gops, void* stream) {
         else if (which == 1) ubench_lds<<<sms, 1024, 0, s>>>(d, iters);
         else if (which == 2) ubench_lds_wide<2><<<sms, 1024, 0, s>>>(d, iters);
         else if (which == 3) ubench_lds_wide<4><<<sms, 1024, 0, s>>>(d, iters);
-        else ubench_ldc<<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 4) ubench_ldc<<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 5) ubench_shfl<0><<<sms, 1024, 0, s>>>(d, iters);
+        else ubench_shfl<1><<<sms, 1024, 0, s>>>(d, iters);
         MG_CUDA(cudaEventRecord(e1, s));
         MG_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
         MG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : which == 1 ? 32.0 : 16.0);   // load INSTRUCTIONS per lane
+        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : which == 1 ? 32.0 : which == 6 ? 32.0 : 16.0);   // load/shuffle INSTRUCTIONS per lane
         const double r = ops / (ms * 1e-3) / 1e9;
         if (rep > 0 && r > best) best = r;
     }
