@@ -215,6 +215,10 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     }
     // candidate queue between the prefilter and the verifier pass
     h.cand_cap = 16ull << 20;
+    if (const char* cap_env = getenv("MG_QUEUE_CAP")) {          // tests shrink the queue to exercise the re-cut path
+        const long long v = atoll(cap_env);
+        if (v >= 8) h.cand_cap = (unsigned long long)v;
+    }
     MG_CUDA(dev_alloc((void**)&h.cand, sizeof(Cand) * h.cand_cap, s));
     MG_CUDA(dev_alloc((void**)&h.cand_count, 8, s));
     MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
@@ -280,7 +284,9 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     {   // a small probe slice first: its survivor density sizes the remaining slices, so that an overflow (a wasted
         // prefilter pass) only happens when the density is very uneven
         const int64_t len = we - wb, probe = len / 64;
-        if (probe >= (1 << 16)) { todo.emplace_back(wb + probe, we); todo.emplace_back(wb, wb + probe); }
+        int64_t probe_min = 1 << 16;
+        if (const char* pm = getenv("MG_PROBE_MIN")) probe_min = atoll(pm) > 0 ? atoll(pm) : probe_min;
+        if (probe >= probe_min) { todo.emplace_back(wb + probe, we); todo.emplace_back(wb, wb + probe); }
         else todo.emplace_back(wb, we);
     }
     bool planned = todo.size() < 2;

@@ -251,3 +251,99 @@ def test_three_hundred_thousand_queries(L):
         want = c_oracle.screen_hamming(contigs, [(0, 100, 300)], grnas, M, threads=16)
         assert np.array_equal(got, want), M
         assert (got > 0).sum() > 300
+
+
+def _resident_counts(L, genome, q, crit, pam):
+    import torch
+    counts = torch.zeros(2 * q.n, dtype=torch.int32, device="cuda")
+    L.screen(genome, q, crit, pam, counts.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return counts.cpu().numpy().astype(np.int64)
+
+
+def _medium_world(L, seed, n_grna, glen=20):
+    rng = random.Random(seed)
+    contigs = [("a", _random_contig(rng, 180000, "ACGT" * 12 + "N")), ("b", _random_contig(rng, 90000)), ("c", _random_contig(rng, 700))]
+    grnas = []
+    for i in range(n_grna):
+        _, seq = contigs[i % 2]
+        p = rng.randrange(0, len(seq) - glen - 2)
+        g = list(seq[p:p + glen].replace("N", "T"))
+        for _ in range(i % 5):
+            g[rng.randrange(glen)] = rng.choice("ACGT")
+        if i % 3 == 0:                       # one gap
+            k = rng.randrange(2, glen - 2)
+            g = g[:k] + g[k + 1:] + [rng.choice("ACGT")] if i % 2 else g[:k] + [rng.choice("ACGT")] + g[k:glen - 1]
+        g = "".join(g)
+        grnas.append(O.reverse_complement(g) if i % 4 == 1 else g)
+    genome = L.Genome.from_contigs(contigs)
+    genome.set_masks([(0, 1000, 1500), (1, 0, 300)])
+    return genome, L.Queries(grnas)
+
+
+def test_results_do_not_depend_on_the_survivor_queue(L):
+    """The verifier queue is sliced by a probe and re-cut on overflow; a tiny queue must give the same counts."""
+    from minorg_b200.ot_regex import make_criteria
+    from minorg_b200.pam import PAM
+    genome, q = _medium_world(L, 31, 96)
+    pam = PAM(".NGG", 20).program()
+    cases = [make_criteria(ot_mismatch=5, ot_pamless=False, grna_length=20),
+             make_criteria(ot_mismatch=3, ot_gap=2, grna_length=20),
+             make_criteria(ot_pattern="0mg-10,1mg-11-", ot_gap=2, grna_length=20),
+             make_criteria(ot_pattern="1mg1-", ot_gap=2, grna_length=20)]
+    try:
+        for crit in cases:
+            os.environ.pop("MG_QUEUE_CAP", None)
+            os.environ.pop("MG_PROBE_MIN", None)
+            want = _resident_counts(L, genome, q, crit, pam)
+            assert want.sum() > 0
+            for cap, probe in (("61", "500"), ("9", "64"), ("4000", "3")):
+                os.environ["MG_QUEUE_CAP"], os.environ["MG_PROBE_MIN"] = cap, probe
+                assert np.array_equal(_resident_counts(L, genome, q, crit, pam), want), (cap, probe)
+    finally:
+        os.environ.pop("MG_QUEUE_CAP", None)
+        os.environ.pop("MG_PROBE_MIN", None)
+        q.free()
+        genome.free()
+
+
+def test_gapped_prefilters_agree(L):
+    """Two independent edit-distance prefilters (bit-sliced rows vs one-pattern-per-thread Myers) must hand the
+    verifier the same anchors: identical counts over ~10^8 cells."""
+    from minorg_b200.ot_regex import make_criteria
+    genome, q = _medium_world(L, 32, 160)
+    try:
+        for kw in (dict(ot_mismatch=2, ot_gap=2), dict(ot_mismatch=5, ot_gap=2), dict(ot_mismatch=3, ot_gap=3),
+                   dict(ot_pattern="2mg1-", ot_gap=2)):
+            crit = make_criteria(grna_length=20, **kw)
+            os.environ.pop("MG_GAPPED_PREFILTER", None)
+            rows = _resident_counts(L, genome, q, crit, None)
+            os.environ["MG_GAPPED_PREFILTER"] = "myers"
+            myers = _resident_counts(L, genome, q, crit, None)
+            assert np.array_equal(rows, myers), kw
+            assert rows.sum() > 0
+    finally:
+        os.environ.pop("MG_GAPPED_PREFILTER", None)
+        q.free()
+        genome.free()
+
+
+def test_scan_kernels_agree(L):
+    """Pair-word scan (default), per-position early-out scan and the per-cell XOR/POPC kernel: same counts, for
+    budgets with and without compile-time specialisation, two gRNA lengths."""
+    from minorg_b200.ot_regex import make_criteria
+    try:
+        for glen in (20, 23, 17):
+            genome, q = _medium_world(L, 40 + glen, 128, glen)
+            for M in (0, 1, 2, 4, 5, 7):
+                crit = make_criteria(ot_mismatch=M + 1)
+                got = {}
+                for mode in ("pairs", "singles", "popc"):
+                    os.environ["MG_SCAN"] = mode
+                    got[mode] = _resident_counts(L, genome, q, crit, None)
+                assert np.array_equal(got["pairs"], got["popc"]) and np.array_equal(got["singles"], got["popc"]), (glen, M)
+                assert got["popc"].sum() > 0
+            q.free()
+            genome.free()
+    finally:
+        os.environ.pop("MG_SCAN", None)
