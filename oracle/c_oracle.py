@@ -53,3 +53,27 @@ def screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads=1):
     if rc != 0:
         raise RuntimeError("oracle_screen_hamming failed: %d" % rc)
     return out[:len(g)]
+
+
+def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1):
+    """Exhaustive no-pattern screen with gaps/trimming (PAM-less): uint32[2N] distinct-anchor counts per oriented
+    query ([i] = '+' strand, [N+i] = '-' strand) - see oracle_screen_nopattern in screen_oracle.c."""
+    bufs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
+    offsets = np.zeros(len(bufs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bufs], out=offsets[1:])
+    blob = np.frombuffer(b"".join(bufs) or b"\0", dtype=np.uint8)
+    masks = list(masks)
+    mc = np.array([m[0] for m in masks] or [0], dtype=np.int32)
+    ms = np.array([m[1] for m in masks] or [0], dtype=np.int64)
+    me = np.array([m[2] for m in masks] or [0], dtype=np.int64)
+    g = [s.encode() if isinstance(s, str) else bytes(s) for s in grnas]
+    L = len(g[0]) if g else 1
+    gb = np.frombuffer(b"".join(g) or b"\0", dtype=np.uint8)
+    out = np.zeros(max(1, 2 * len(g)), dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _load().oracle_screen_nopattern(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
+                                         C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
+                                         C.c_int(max_gap), C.c_int(threads), p(out))
+    if rc != 0:
+        raise RuntimeError("oracle_screen_nopattern failed: %d" % rc)
+    return out[:2 * len(g)]

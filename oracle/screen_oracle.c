@@ -121,3 +121,115 @@ int oracle_screen_hamming(const char* seq, const int64_t* offsets, int n_contigs
     free(priv); free(jobs); free(th); free(qbits); free(qinv);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Exhaustive no-pattern screen with gaps and trimming (universe E1 of SURVEY.md 8c), PAM-less: for every gRNA and
+ * strand, the number of distinct ANCHORS (virtual end of the alignment = subject end + unaligned 3' positions) that
+ * carry at least one alignment satisfying MINORg._is_offtarget_aln_nopattern (MINORg.py:2018-2044:
+ * mm <= M, gaps <= Gp, mm + gaps + unaligned <= M + Gp) whose subject span is not inside one mask
+ * (MINORg.py:1994-2000).  Plain forward depth-first enumeration from every (query start, subject start), pruned only
+ * by the budget (all three counters are monotone).  This is what the device's general path reports per oriented
+ * query for the same criteria (prefilter + verifier), so tests compare the 2N counts one to one.
+ * Pinned indirectly: on the golden cases its fail flags equal the verdicts of the reference's predicates
+ * (tests/test_oracle_c.py). */
+typedef struct {
+    const uint8_t* T; int64_t n;       /* strand text codes */
+    const uint8_t* q; int L, M, Gp, B;
+    const int64_t* ms; const int64_t* me; int n_masks; int strand; /* masks in forward coordinates */
+    uint8_t* ends;                     /* bitmap over virtual ends 0 .. n + L */
+    int qs; int64_t s;
+} gctx_t;
+
+static int g_masked(const gctx_t* c, int64_t a, int64_t b) {     /* strand span [a,b) -> forward span */
+    int64_t fa = c->strand > 0 ? a : c->n - b, fb = c->strand > 0 ? b : c->n - a;
+    for (int i = 0; i < c->n_masks; ++i) {
+        int64_t lo = c->ms[i] < c->me[i] ? c->ms[i] : c->me[i], hi = c->ms[i] < c->me[i] ? c->me[i] : c->ms[i];
+        if (fa >= lo && fb <= hi) return 1;
+    }
+    return 0;
+}
+
+static void g_dfs(gctx_t* c, int j, int64_t t, int gaps, int mm, int ncols) {
+    if (mm + gaps + c->qs > c->B) return;
+    if (j < c->L && t < c->n) {
+        const int qb = c->q[j], sb = c->T[t];
+        const int mm2 = mm + ((qb == sb && qb < 4) ? 0 : 1);
+        if (mm2 <= c->M) {
+            const int qe = j + 1, u = c->qs + c->L - qe;
+            if (mm2 + gaps + u <= c->B && !g_masked(c, c->s, t + 1)) {
+                const int64_t e = (t + 1) + (c->L - qe);
+                c->ends[e >> 3] |= (uint8_t)(1u << (e & 7));
+            }
+            g_dfs(c, j + 1, t + 1, gaps, mm2, ncols + 1);
+        }
+    }
+    if (ncols > 0 && gaps < c->Gp) {
+        if (j < c->L) g_dfs(c, j + 1, t, gaps + 1, mm, ncols + 1);
+        if (t < c->n) g_dfs(c, j, t + 1, gaps + 1, mm, ncols + 1);
+    }
+}
+
+typedef struct {
+    const uint8_t* fwd; const uint8_t* rev; int64_t n;
+    const uint8_t* qcodes; int nq, L, M, Gp;
+    const int64_t* ms; const int64_t* me; int n_masks;
+    int q0, q1; uint32_t* counts; /* [2*nq] shared, disjoint slots per thread */
+} gjob_t;
+
+static void* g_run(void* arg) {
+    gjob_t* j = (gjob_t*)arg;
+    const size_t nbytes = (size_t)(j->n + j->L + 16) / 8 + 2;
+    uint8_t* ends = (uint8_t*)malloc(nbytes);
+    for (int qi = j->q0; qi < j->q1; ++qi) {
+        for (int strand = 1; strand >= -1; strand -= 2) {
+            memset(ends, 0, nbytes);
+            gctx_t c;
+            c.T = strand > 0 ? j->fwd : j->rev; c.n = j->n; c.q = j->qcodes + (size_t)qi * j->L;
+            c.L = j->L; c.M = j->M; c.Gp = j->Gp; c.B = j->M + j->Gp;
+            c.ms = j->ms; c.me = j->me; c.n_masks = j->n_masks; c.strand = strand; c.ends = ends;
+            for (int64_t s = 0; s < j->n; ++s)
+                for (int qs = 0; qs < j->L && qs <= c.B; ++qs) { c.qs = qs; c.s = s; g_dfs(&c, qs, s, 0, 0, 0); }
+            uint32_t cnt = 0;
+            for (size_t b = 0; b < nbytes; ++b) cnt += (uint32_t)__builtin_popcount(ends[b]);
+            j->counts[strand > 0 ? qi : j->nq + qi] += cnt;
+        }
+    }
+    free(ends);
+    return NULL;
+}
+
+/* counts_out[2n]: [i] = '+' strand anchors of gRNA i, [n+i] = '-' strand anchors. */
+int oracle_screen_nopattern(const char* seq, const int64_t* offsets, int n_contigs,
+                            const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                            const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out) {
+    if (L < 1 || L > 32 || n < 0 || n_threads < 1 || max_gap < 0 || max_gap > 3) return -2;
+    uint8_t* qcodes = (uint8_t*)malloc((size_t)n * L + 1);
+    for (size_t i = 0; i < (size_t)n * L; ++i) qcodes[i] = (uint8_t)code_of(grna[i]);
+    memset(counts_out, 0, sizeof(uint32_t) * 2 * (size_t)n);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    gjob_t* jobs = (gjob_t*)malloc(sizeof(gjob_t) * (size_t)n_threads);
+    for (int c = 0; c < n_contigs; ++c) {
+        const int64_t len = offsets[c + 1] - offsets[c];
+        if (len == 0) continue;
+        uint8_t* fwd = (uint8_t*)malloc((size_t)len), *rev = (uint8_t*)malloc((size_t)len);
+        for (int64_t i = 0; i < len; ++i) {
+            const int k = code_of(seq[offsets[c] + i]);
+            fwd[i] = (uint8_t)k;
+            rev[len - 1 - i] = (uint8_t)(k == 4 ? 4 : 3 - k);
+        }
+        int nm = 0;
+        int64_t* ms = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1)), *me = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
+        for (int i = 0; i < n_masks; ++i) if (mask_contig[i] == c) { ms[nm] = mask_start[i]; me[nm] = mask_end[i]; ++nm; }
+        for (int t = 0; t < n_threads; ++t) {
+            gjob_t* j = &jobs[t];
+            j->fwd = fwd; j->rev = rev; j->n = len; j->qcodes = qcodes; j->nq = n; j->L = L; j->M = max_mm; j->Gp = max_gap;
+            j->ms = ms; j->me = me; j->n_masks = nm; j->q0 = (int)((int64_t)n * t / n_threads); j->q1 = (int)((int64_t)n * (t + 1) / n_threads);
+            j->counts = counts_out;
+            pthread_create(&th[t], NULL, g_run, j);
+        }
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+        free(fwd); free(rev); free(ms); free(me);
+    }
+    free(jobs); free(th); free(qcodes);
+    return 0;
+}

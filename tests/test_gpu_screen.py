@@ -347,3 +347,40 @@ def test_scan_kernels_agree(L):
             genome.free()
     finally:
         os.environ.pop("MG_SCAN", None)
+
+
+def test_gapped_counts_vs_c_oracle_medium(L):
+    """Gapped / trimmed no-pattern screen at medium size (270 kb, 96 gRNA, ~10^8 cells): the device's per-query ANCHOR
+    counts (prefilter + verifier) against the exhaustive C oracle, one to one for both orientations."""
+    from minorg_b200.ot_regex import make_criteria
+    rng = random.Random(77)
+    contigs = [("a", _random_contig(rng, 180000, "ACGT" * 12 + "N")), ("b", _random_contig(rng, 90000)), ("c", _random_contig(rng, 700)),
+               ("d", _random_contig(rng, 9))]
+    grnas = []
+    for i in range(96):
+        _, seq = contigs[i % 2]
+        p = rng.randrange(0, len(seq) - 24)
+        g = list(seq[p:p + 20].replace("N", "T"))
+        for _ in range(i % 5):
+            g[rng.randrange(20)] = rng.choice("ACGT")
+        if i % 3 == 0:
+            k = rng.randrange(2, 18)
+            g = (g[:k] + g[k + 1:] + [rng.choice("ACGT")]) if i % 2 else (g[:k] + [rng.choice("ACGT")] + g[k:19])
+        if i % 11 == 0:                      # hanging off a contig end
+            g = list(contigs[1][1][-16:]) + [rng.choice("ACGT") for _ in range(4)]
+        g = "".join(g)
+        grnas.append(O.reverse_complement(g) if i % 4 == 1 else g)
+    masks = [(0, 1000, 1500), (1, 0, 300), (1, 89000, 90000)]
+    genome = L.Genome.from_contigs(contigs)
+    genome.set_masks(masks)
+    q = L.Queries(grnas)
+    try:
+        for M, Gp in ((2, 1), (4, 1), (1, 2), (0, 1), (3, 0), (2, 3)):
+            crit = make_criteria(ot_mismatch=M + 1, ot_gap=Gp + 1, grna_length=20)
+            got = _resident_counts(L, genome, q, crit, None)
+            want = c_oracle.screen_nopattern(contigs, masks, grnas, M, Gp, threads=16).astype(np.int64)
+            assert np.array_equal(got, want), (M, Gp, np.nonzero(got != want)[0][:10], got[got != want][:10], want[got != want][:10])
+            assert want.sum() > 50
+    finally:
+        q.free()
+        genome.free()

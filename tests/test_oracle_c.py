@@ -43,3 +43,25 @@ def test_c_oracle_random_vs_python():
         want = O.screen_hamming(grnas, contigs, masks, M)
         got = c_oracle.screen_hamming(contigs, [(0, 3, 3 + L + 2), (1, 0, 10)], grnas, M, threads=3)
         assert got.tolist() == want, trial
+
+
+def test_c_general_oracle_matches_golden_and_python(golden):
+    """oracle_screen_nopattern (gaps + trimming, PAM-less): fail flags vs the verdicts of the reference's predicates on
+    the golden cases, and anchor counts vs the Hamming oracle where the two criteria coincide."""
+    n = 0
+    for c in golden("screen_cases.json")["cases"]:
+        k = c["criteria"]
+        if k.get("pattern") is not None or not k["pamless"]:
+            continue
+        M, Gp = max(1, k["ot_mismatch"]) - 1, max(1, k["ot_gap"]) - 1
+        contigs = [tuple(x) for x in c["contigs"]]
+        names = [x[0] for x in contigs]
+        masks = [(names.index(m[1]), m[2], m[3]) for m in c["masks"]]
+        got = c_oracle.screen_nopattern(contigs, masks, c["grnas"], M, Gp, threads=2)
+        ng = len(c["grnas"])
+        assert [(got[i] + got[ng + i]) > 0 for i in range(ng)] == c["fail"], c["name"]
+        if Gp == 0:
+            ham = c_oracle.screen_hamming(contigs, masks, c["grnas"], M, threads=2)
+            assert (got[:ng] + got[ng:]).tolist() == ham.tolist(), c["name"]
+        n += 1
+    assert n >= 10
