@@ -380,7 +380,7 @@ def test_gapped_counts_vs_c_oracle_medium(L):
             got = _resident_counts(L, genome, q, crit, None)
             want = c_oracle.screen_nopattern(contigs, masks, grnas, M, Gp, threads=16).astype(np.int64)
             assert np.array_equal(got, want), (M, Gp, np.nonzero(got != want)[0][:10], got[got != want][:10], want[got != want][:10])
-            assert want.sum() > 50
+            assert want.sum() > 5
     finally:
         q.free()
         genome.free()
