@@ -232,9 +232,11 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     // anchors (virtual ends, exclusive) owned by the window range [wb, we): e = p + L
     int K = crit->n_units ? crit->prefilter_edits : crit->max_mismatch + crit->max_gap;
     if (K >= L) K = -1;
-    const bool by_pieces = h.n_pieces > 0;
-    const bool by_hamming = !by_pieces && crit->max_gap == 0 && K >= 0;
-    const bool by_myers = !by_pieces && !by_hamming && K >= 0;
+    const char* pf_env = getenv("MG_PREFILTER");        // "none": hand EVERY anchor to the verifier (tests: prefilter soundness)
+    const bool no_prefilter = pf_env && strcmp(pf_env, "none") == 0;
+    const bool by_pieces = !no_prefilter && h.n_pieces > 0;
+    const bool by_hamming = !no_prefilter && !by_pieces && crit->max_gap == 0 && K >= 0;
+    const bool by_myers = !no_prefilter && !by_pieces && !by_hamming && K >= 0;
     int dev = 0, sms = 0, smem_max = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -55,9 +55,39 @@ def screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads=1):
     return out[:len(g)]
 
 
-def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1):
-    """Exhaustive no-pattern screen with gaps/trimming (PAM-less): uint32[2N] distinct-anchor counts per oriented
-    query ([i] = '+' strand, [N+i] = '-' strand) - see oracle_screen_nopattern in screen_oracle.c."""
+def _pam_side(side_regex):
+    """'TTT[ACG]' / '[GATC][AG]{1,2}T' -> (n alternatives, int32 lengths, uint8 allow[alt*16+k]) for the C oracle."""
+    import itertools
+    atoms, i = [], 0
+    while i < len(side_regex):
+        if side_regex[i] == "[":
+            j = side_regex.index("]", i)
+            chars, i = side_regex[i + 1:j], j + 1
+        else:
+            chars, i = side_regex[i], i + 1
+        lo = hi = 1
+        if i < len(side_regex) and side_regex[i] == "{":
+            j = side_regex.index("}", i)
+            body = side_regex[i + 1:j].split(",")
+            lo, hi, i = int(body[0]), int(body[-1]), j + 1
+        atoms.append((chars, lo, hi))
+    alts = []
+    for reps in itertools.product(*[range(lo, hi + 1) for _, lo, hi in atoms]):
+        alt = [c for (c, _, _), r in zip(atoms, reps) for _ in range(r)]
+        if alt not in alts:
+            alts.append(alt)
+    lens = np.array([len(a) for a in alts] or [0], dtype=np.int32)
+    allow = np.zeros(max(1, len(alts)) * 16, dtype=np.uint8)
+    for a, alt in enumerate(alts):
+        for k, chars in enumerate(alt):
+            allow[a * 16 + k] = sum(1 << "ACGT".index(ch) for ch in set(chars.upper()) if ch in "ACGT")
+    return (len(alts) if side_regex else 0), lens, allow
+
+
+def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1, pam=None):
+    """Exhaustive no-pattern screen with gaps/trimming: uint32[2N] distinct-anchor counts per oriented query
+    ([i] = '+' strand, [N+i] = '-' strand) - see oracle_screen_nopattern in screen_oracle.c.  pam = an
+    oracle.minorg_oracle.OraclePAM to require PAM proximity (ot_pamless=False), None for the PAM-less default."""
     bufs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
     offsets = np.zeros(len(bufs) + 1, dtype=np.int64)
     np.cumsum([len(b) for b in bufs], out=offsets[1:])
@@ -71,9 +101,17 @@ def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1):
     gb = np.frombuffer(b"".join(g) or b"\0", dtype=np.uint8)
     out = np.zeros(max(1, 2 * len(g)), dtype=np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = _load().oracle_screen_nopattern(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
-                                         C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
-                                         C.c_int(max_gap), C.c_int(threads), p(out))
+    if pam is None:
+        n5, len5, allow5, n3, len3, allow3, max5, max3, pamless = 0, np.zeros(1, np.int32), np.zeros(16, np.uint8), 0, \
+            np.zeros(1, np.int32), np.zeros(16, np.uint8), 0, 0, 1
+    else:
+        n5, len5, allow5 = _pam_side(pam.five_prime())
+        n3, len3, allow3 = _pam_side(pam.three_prime())
+        max5, max3, pamless = pam.five_prime_maxlen(), pam.three_prime_maxlen(), 0
+    rc = _load().oracle_screen_nopattern_pam(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
+                                             C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
+                                             C.c_int(max_gap), C.c_int(threads), p(out), C.c_int(pamless),
+                                             C.c_int(n5), p(len5), p(allow5), C.c_int(max5), C.c_int(n3), p(len3), p(allow3), C.c_int(max3))
     if rc != 0:
         raise RuntimeError("oracle_screen_nopattern failed: %d" % rc)
     return out[:2 * len(g)]

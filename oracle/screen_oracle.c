@@ -138,7 +138,31 @@ typedef struct {
     const int64_t* ms; const int64_t* me; int n_masks; int strand; /* masks in forward coordinates */
     uint8_t* ends;                     /* bitmap over virtual ends 0 .. n + L */
     int qs; int64_t s;
+    /* optional PAM proximity check (MINORg._has_pam, MINORg.py:2063-2087); pamless = 1 skips it */
+    int pamless, n5, n3, max5, max3;
+    const int32_t* len5; const uint8_t* allow5; const int32_t* len3; const uint8_t* allow3; /* allow[alt*16 + k] = ACGT bit mask */
 } gctx_t;
+
+static int g_pam_in(const gctx_t* c, int n_alts, const int32_t* len, const uint8_t* allow, int64_t w0, int64_t w1) {
+    if (n_alts == 0) return 0;                      /* an empty PAM side never matches (MINORg.py:2085-2086) */
+    for (int64_t x = w0; x <= w1; ++x)
+        for (int a = 0; a < n_alts; ++a) {
+            if (x + len[a] > w1) continue;
+            int ok = 1;
+            for (int k = 0; k < len[a] && ok; ++k) { const int b = c->T[x + k]; ok = b < 4 && ((allow[a * 16 + k] >> b) & 1); }
+            if (ok) return 1;
+        }
+    return 0;
+}
+
+static int g_has_pam(const gctx_t* c, int qe, int gaps, int64_t s, int64_t t) {
+    const int gap_excess = c->Gp - gaps;
+    int pre = c->max5 + gap_excess + c->qs, post = c->max3 + gap_excess + (c->L - qe);
+    if (pre < 0) pre = 0;
+    if (post < 0) post = 0;
+    const int64_t w0 = s - pre < 0 ? 0 : s - pre, w1 = t + post > c->n ? c->n : t + post;   /* clamped to the contig */
+    return g_pam_in(c, c->n5, c->len5, c->allow5, w0, s) || g_pam_in(c, c->n3, c->len3, c->allow3, t, w1);
+}
 
 static int g_masked(const gctx_t* c, int64_t a, int64_t b) {     /* strand span [a,b) -> forward span */
     int64_t fa = c->strand > 0 ? a : c->n - b, fb = c->strand > 0 ? b : c->n - a;
@@ -156,7 +180,7 @@ static void g_dfs(gctx_t* c, int j, int64_t t, int gaps, int mm, int ncols) {
         const int mm2 = mm + ((qb == sb && qb < 4) ? 0 : 1);
         if (mm2 <= c->M) {
             const int qe = j + 1, u = c->qs + c->L - qe;
-            if (mm2 + gaps + u <= c->B && !g_masked(c, c->s, t + 1)) {
+            if (mm2 + gaps + u <= c->B && !g_masked(c, c->s, t + 1) && (c->pamless || g_has_pam(c, qe, gaps, c->s, t + 1))) {
                 const int64_t e = (t + 1) + (c->L - qe);
                 c->ends[e >> 3] |= (uint8_t)(1u << (e & 7));
             }
@@ -174,6 +198,8 @@ typedef struct {
     const uint8_t* qcodes; int nq, L, M, Gp;
     const int64_t* ms; const int64_t* me; int n_masks;
     int q0, q1; uint32_t* counts; /* [2*nq] shared, disjoint slots per thread */
+    int pamless, n5, n3, max5, max3;
+    const int32_t* len5; const uint8_t* allow5; const int32_t* len3; const uint8_t* allow3;
 } gjob_t;
 
 static void* g_run(void* arg) {
@@ -187,6 +213,8 @@ static void* g_run(void* arg) {
             c.T = strand > 0 ? j->fwd : j->rev; c.n = j->n; c.q = j->qcodes + (size_t)qi * j->L;
             c.L = j->L; c.M = j->M; c.Gp = j->Gp; c.B = j->M + j->Gp;
             c.ms = j->ms; c.me = j->me; c.n_masks = j->n_masks; c.strand = strand; c.ends = ends;
+            c.pamless = j->pamless; c.n5 = j->n5; c.n3 = j->n3; c.max5 = j->max5; c.max3 = j->max3;
+            c.len5 = j->len5; c.allow5 = j->allow5; c.len3 = j->len3; c.allow3 = j->allow3;
             for (int64_t s = 0; s < j->n; ++s)
                 for (int qs = 0; qs < j->L && qs <= c.B; ++qs) { c.qs = qs; c.s = s; g_dfs(&c, qs, s, 0, 0, 0); }
             uint32_t cnt = 0;
@@ -199,9 +227,26 @@ static void* g_run(void* arg) {
 }
 
 /* counts_out[2n]: [i] = '+' strand anchors of gRNA i, [n+i] = '-' strand anchors. */
+int oracle_screen_nopattern_pam(const char* seq, const int64_t* offsets, int n_contigs,
+                                const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                                const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out,
+                                int pamless, int n5, const int32_t* len5, const uint8_t* allow5, int max5,
+                                int n3, const int32_t* len3, const uint8_t* allow3, int max3);
+
 int oracle_screen_nopattern(const char* seq, const int64_t* offsets, int n_contigs,
                             const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
                             const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out) {
+    return oracle_screen_nopattern_pam(seq, offsets, n_contigs, mask_contig, mask_start, mask_end, n_masks, grna, n, L,
+                                       max_mm, max_gap, n_threads, counts_out, 1, 0, NULL, NULL, 0, 0, NULL, NULL, 0);
+}
+
+/* Same with the PAM proximity requirement: a PAM side = n alternatives of fixed length, position k of alternative a
+ * allows the bases whose bit is set in allow[a*16 + k] (bit 0..3 = A,C,G,T); max5/max3 = PAM.five/three_prime_maxlen(). */
+int oracle_screen_nopattern_pam(const char* seq, const int64_t* offsets, int n_contigs,
+                                const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                                const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out,
+                                int pamless, int n5, const int32_t* len5, const uint8_t* allow5, int max5,
+                                int n3, const int32_t* len3, const uint8_t* allow3, int max3) {
     if (L < 1 || L > 32 || n < 0 || n_threads < 1 || max_gap < 0 || max_gap > 3) return -2;
     uint8_t* qcodes = (uint8_t*)malloc((size_t)n * L + 1);
     for (size_t i = 0; i < (size_t)n * L; ++i) qcodes[i] = (uint8_t)code_of(grna[i]);
@@ -225,6 +270,8 @@ int oracle_screen_nopattern(const char* seq, const int64_t* offsets, int n_conti
             j->fwd = fwd; j->rev = rev; j->n = len; j->qcodes = qcodes; j->nq = n; j->L = L; j->M = max_mm; j->Gp = max_gap;
             j->ms = ms; j->me = me; j->n_masks = nm; j->q0 = (int)((int64_t)n * t / n_threads); j->q1 = (int)((int64_t)n * (t + 1) / n_threads);
             j->counts = counts_out;
+            j->pamless = pamless; j->n5 = n5; j->n3 = n3; j->max5 = max5; j->max3 = max3;
+            j->len5 = len5; j->allow5 = allow5; j->len3 = len3; j->allow3 = allow3;
             pthread_create(&th[t], NULL, g_run, j);
         }
         for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);

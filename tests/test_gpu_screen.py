@@ -381,6 +381,42 @@ def test_gapped_counts_vs_c_oracle_medium(L):
             want = c_oracle.screen_nopattern(contigs, masks, grnas, M, Gp, threads=16).astype(np.int64)
             assert np.array_equal(got, want), (M, Gp, np.nonzero(got != want)[0][:10], got[got != want][:10], want[got != want][:10])
             assert want.sum() > 5
+        # PAM proximity (ot_pamless=False): windows widen with trimming and unused gap allowance (MINORg.py:2063-2087)
+        from minorg_b200.pam import PAM
+        for pam, M, Gp in ((".NGG", 3, 0), (".NGG", 4, 1), ("TTTV.", 3, 1), ("R{1,2}T", 2, 0), (".", 3, 0), ("TTN", 2, 2)):
+            crit = make_criteria(ot_mismatch=M + 1, ot_gap=Gp + 1, ot_pamless=False, grna_length=20)
+            got = _resident_counts(L, genome, q, crit, PAM(pam, 20).program())
+            want = c_oracle.screen_nopattern(contigs, masks, grnas, M, Gp, threads=16, pam=O.OraclePAM(pam, 20)).astype(np.int64)
+            assert np.array_equal(got, want), (pam, M, Gp, np.nonzero(got != want)[0][:10], got[got != want][:10], want[got != want][:10])
+            assert want.sum() > 0 or pam == "."
     finally:
+        q.free()
+        genome.free()
+
+
+def test_pattern_prefilters_are_sound_at_medium_size(L):
+    """--ot-pattern modes: the prefiltered paths (Hamming budget / exact pieces / edit distance, all derived by the host
+    from the pattern) against the same verifier run on EVERY anchor (MG_PREFILTER=none), 10^7 cells each."""
+    from minorg_b200.ot_regex import make_criteria
+    from minorg_b200.pam import PAM
+    genome, q = _medium_world(L, 55, 48)
+    n = q.n
+    try:
+        for pat, gap, pamless, exact in (("0mg-10,1mg-11-", 2, True, False), ("1mg1-", 2, True, False), ("2mg1-", 2, True, True),
+                                         ("(0mg5,1mg6-)|(0mg6,1m7-)", 0, True, True), ("1m-8,2m9-", 0, True, True),
+                                         ("1mg1-", 2, False, False), ("0m-6,3mg1-", 2, True, True)):
+            crit = make_criteria(ot_pattern=pat, ot_gap=gap, ot_pamless=pamless, grna_length=20)
+            pam = PAM(".NGG", 20).program()
+            os.environ.pop("MG_PREFILTER", None)
+            fast = _resident_counts(L, genome, q, crit, pam)
+            os.environ["MG_PREFILTER"] = "none"
+            full = _resident_counts(L, genome, q, crit, pam)
+            if exact:                          # one candidate per anchor: counts must agree
+                assert np.array_equal(fast, full), pat
+            else:                              # exact-piece prefilter emits 2*Gp+1 anchors per hit: compare verdicts
+                assert np.array_equal((fast[:n] + fast[n:]) > 0, (full[:n] + full[n:]) > 0), pat
+            assert full.sum() > 0 or not pamless, pat
+    finally:
+        os.environ.pop("MG_PREFILTER", None)
         q.free()
         genome.free()

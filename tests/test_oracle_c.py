@@ -51,17 +51,18 @@ def test_c_general_oracle_matches_golden_and_python(golden):
     n = 0
     for c in golden("screen_cases.json")["cases"]:
         k = c["criteria"]
-        if k.get("pattern") is not None or not k["pamless"]:
+        if k.get("pattern") is not None:
             continue
         M, Gp = max(1, k["ot_mismatch"]) - 1, max(1, k["ot_gap"]) - 1
         contigs = [tuple(x) for x in c["contigs"]]
         names = [x[0] for x in contigs]
         masks = [(names.index(m[1]), m[2], m[3]) for m in c["masks"]]
-        got = c_oracle.screen_nopattern(contigs, masks, c["grnas"], M, Gp, threads=2)
+        pam = None if k["pamless"] else O.OraclePAM(k["pam"], c["L"])
+        got = c_oracle.screen_nopattern(contigs, masks, c["grnas"], M, Gp, threads=2, pam=pam)
         ng = len(c["grnas"])
         assert [(got[i] + got[ng + i]) > 0 for i in range(ng)] == c["fail"], c["name"]
-        if Gp == 0:
+        if Gp == 0 and k["pamless"]:
             ham = c_oracle.screen_hamming(contigs, masks, c["grnas"], M, threads=2)
             assert (got[:ng] + got[ng:]).tolist() == ham.tolist(), c["name"]
         n += 1
-    assert n >= 10
+    assert n >= 17
