@@ -132,7 +132,7 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
 #pragma unroll
                     for (int j = 0; j < T1; ++j) x1[j] = *reinterpret_cast<const uint32_t*>(t + off[j]);
                     uint32_t part[NB1];
-                    mgcsa::csa_count<T1>(x1, part);
+                    mgcsa::csa_count<T1>(x1, part);             // the exact partial count is reused by the second stage
                     const uint32_t alive = (K >= 0) ? le_const_impl<NB1>(part, K) : le_runtime<NB1>(part, kthr);
                     ++n_steps;
                     if (!__any_sync(0xFFFFFFFFu, alive != 0u)) continue;
@@ -162,35 +162,6 @@ screen_bitsliced_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_
         atomicAdd(stats, (unsigned long long)n_steps);
         atomicAdd(stats + 1, (unsigned long long)n_stage2);
     }
-}
-
-// Hand-reduced threshold networks for the stage-1 test of the common budgets (the generic path sums to an exact
-// count and then compares; these stop as soon as the verdict is determined).
-// No word set among T inputs: the budget-0 (exact match) test.
-template <int T>
-__device__ __forceinline__ uint32_t none_set(const uint32_t (&x)[T]) {
-    uint32_t acc = x[0];
-#pragma unroll
-    for (int k = 1; k + 1 < T; k += 2) acc = acc | x[k] | x[k + 1];       // one LOP3 per two inputs
-    if ((T & 1) == 0) acc |= x[T - 1];
-    return ~acc;
-}
-// At most 4 of 10 words set (L = 20, <= 4 mismatches): 16 logic ops instead of 19.
-__device__ __forceinline__ uint32_t at_most_4_of_10(const uint32_t (&x)[10]) {
-    using mgcsa::lop3_maj;
-    using mgcsa::lop3_xor3;
-    const uint32_t s1 = lop3_xor3(x[0], x[1], x[2]), c1 = lop3_maj(x[0], x[1], x[2]);
-    const uint32_t s2 = lop3_xor3(x[3], x[4], x[5]), c2 = lop3_maj(x[3], x[4], x[5]);
-    const uint32_t s3 = lop3_xor3(x[6], x[7], x[8]), c3 = lop3_maj(x[6], x[7], x[8]);
-    const uint32_t s4 = lop3_xor3(s1, s2, s3), c4 = lop3_maj(s1, s2, s3);
-    const uint32_t c5 = s4 & x[9];                         // weight-1 leftovers: bit0 = s4 ^ x[9]
-    const uint32_t s6 = lop3_xor3(c1, c2, c3), c6 = lop3_maj(c1, c2, c3);
-    const uint32_t s7 = lop3_xor3(s6, c4, c5), c7 = lop3_maj(s6, c4, c5);
-    // count = bit0 + 2*(s7 + 2*(c6 + c7)) <= 4  <=>  no weight-4 carry, or exactly one and nothing below it
-    uint32_t low, alive;
-    asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(low) : "r"(s7), "r"(s4), "r"(x[9]));      // s7 | (s4 ^ x9)
-    asm("lop3.b32 %0, %1, %2, %3, 0x17;" : "=r"(alive) : "r"(c6), "r"(c7), "r"(low));     // (~c6&~c7) | ((c6^c7)&~low)
-    return alive;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -250,10 +221,8 @@ screen_pairs_kernel(GenomeView gv, QueriesView qv, int kthr, int groups_per_chun
 #pragma unroll
                 for (int k = 0; k < T; ++k) x[k] = *reinterpret_cast<const uint32_t*>(t + off[k]);
                 uint32_t alive;
-                if constexpr (K == 0) {
-                    alive = none_set<T>(x);
-                } else if constexpr (K == 4 && T == 10) {
-                    alive = at_most_4_of_10(x);
+                if constexpr (mgcsa::HasCountLe<T, K>::value) {
+                    alive = mgcsa::count_le<T, K>(x);           // generated threshold network (gen_csa.py): 15 LOP3 for 4-of-10
                 } else {
                     uint32_t part[NBT];
                     mgcsa::csa_count<T>(x, part);

@@ -226,3 +226,84 @@ def test_eqv_matches_reference_up_to_its_hash_order(golden, tmp_path):
                 else:
                     assert float(f[4]) >= seen[-1][1]
                     seen[-1] = (f[0], float(f[4]))
+
+
+def _emulate_enumerator(program, seq, L):
+    """What K2 (csrc/enumerate.cu) computes from a PAM program, restated in Python: starts s such that some
+    5' alternative ends at s and some 3' alternative starts at s+L (byte classes; empty side = no constraint)."""
+    data = seq.encode("latin-1")
+
+    def side_ok(side, at, behind):
+        if side.n_alts == 0:
+            return True
+        for a in range(side.n_alts):
+            n = side.len[a]
+            s = at - n if behind else at
+            if s < 0 or s + n > len(data):
+                continue
+            if all((side.allow[a][k][data[s + k] >> 5] >> (data[s + k] & 31)) & 1 for k in range(n)):
+                return True
+        return False
+    return [s for s in range(len(data) - L + 1) if side_ok(program.five, s, True) and side_ok(program.three, s + L, False)]
+
+
+def test_pam_program_equals_regex_on_random_input():
+    """The device representation of a PAM (finite alternatives of byte classes) selects exactly the starts the
+    reference's regex does (`regex.finditer(..., overlapped=True)`, IGNORECASE), for presets, sets and {m,n} repeats."""
+    import random
+    import regex
+    rng = random.Random(8)
+    pams = [".NGG", "TTTV.", "NGG", "GG", "TTN", ".NGRRT", "R{1,2}T", "T{3}V.", "[AG]GG", ".N[AG]{2}G", "Y{0,2}A.", "DTTN.",
+            ".NNNNRYAC", ".", "A{2,3}.", ".W{1,3}G", "BGG."]
+    for pam in pams:
+        for L in (5, 20):
+            p = PAM(pam, L)
+            prog = p.program()
+            rx = regex.compile(p.regex_string(), regex.IGNORECASE)
+            for _ in range(6):
+                seq = "".join(rng.choice("ACGTacgtNRYn") for _ in range(rng.randrange(0, 90)))
+                want = [m.start() for m in rx.finditer(seq, overlapped=True)]
+                assert _emulate_enumerator(prog, seq, L) == want, (pam, L, seq)
+
+
+def test_generated_threshold_networks_exhaustively():
+    """csrc/csa_gen.cuh: every emitted count_le<T,K> network (T <= 12) is simulated on ALL 2^T inputs (big-int truth
+    vectors through the emitted LOP3 look-up tables) and must equal popcount(inputs) <= K."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "minorg_b200", "csrc", "csa_gen.cuh")).read()
+    funcs = re.findall(r"uint32_t count_le<(\d+), (\d+)>\(const uint32_t \(&x\)\[\d+\]\) \{\n(.*?)\n\}", src, flags=re.S)
+    assert len(funcs) >= 90
+    checked = 0
+    for T, K, body in funcs:
+        T, K = int(T), int(K)
+        if T > 12:
+            continue
+        n = 1 << T
+        full = (1 << n) - 1
+        env = {"0u": 0, "0xFFFFFFFFu": full}
+        for i in range(T):
+            v = 0
+            for a in range(n):
+                if (a >> i) & 1:
+                    v |= 1 << a
+            env["x[%d]" % i] = v
+        result = None
+        for ln in body.splitlines():
+            m = re.match(r"\s+const uint32_t (\w+) = lop3<0x(\w+)>\((.+), (.+), (.+)\);", ln)
+            if m:
+                tt, a, b, c = int(m.group(2), 16), env[m.group(3)], env[m.group(4)], env[m.group(5)]
+                r = 0
+                for idx in range(8):
+                    if (tt >> idx) & 1:
+                        r |= (a if idx & 4 else ~a & full) & (b if idx & 2 else ~b & full) & (c if idx & 1 else ~c & full)
+                env[m.group(1)] = r
+            else:
+                result = env[re.match(r"\s+return (.+);", ln).group(1)]
+        want = 0
+        for a in range(n):
+            if bin(a).count("1") <= K:
+                want |= 1 << a
+        assert result == want, (T, K)
+        checked += 1
+    assert checked >= 60
