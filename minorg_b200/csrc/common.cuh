@@ -56,6 +56,7 @@ struct QueriesView {
     const uint8_t* codes;     // [2N][L] base codes 0..3, 4 = invalid; query N+i = revcomp of gRNA i
     const uint32_t* tab;      // [n_groups][4L+1] bit-sliced mismatch words (+ one all-ones word)
     const uint32_t* tab2;     // [n_groups][16*ceil(L/2)+1] pair words: some base of the position PAIR mismatches
+    const uint4* packed;      // [2N] {2-bit codes of positions 0..15, of 16..31, bit j = position j is not ACGT, 0}
     int n;                    // N
     int len;                  // L
     int n_groups;             // ceil(2N/32)
@@ -130,9 +131,10 @@ struct mg_queries {
     uint8_t* d_codes = nullptr;
     uint32_t* d_tab = nullptr;
     uint32_t* d_tab2 = nullptr;
+    uint4* d_packed = nullptr;
     mg::QueriesView view() const {
         mg::QueriesView v;
-        v.codes = d_codes; v.tab = d_tab; v.tab2 = d_tab2; v.n = n; v.len = len; v.n_groups = n_groups;
+        v.codes = d_codes; v.tab = d_tab; v.tab2 = d_tab2; v.packed = d_packed; v.n = n; v.len = len; v.n_groups = n_groups;
         return v;
     }
 };

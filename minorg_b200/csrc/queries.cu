@@ -64,6 +64,19 @@ __global__ void query_pair_table_kernel(const uint32_t* __restrict__ tab, int le
     tab2[idx] = w;
 }
 
+// packed[q] = 2-bit codes (position j at bits 2j of the 64-bit x:y) and the mask of non-ACGT positions
+__global__ void query_pack_kernel(const uint8_t* __restrict__ codes, int nq, int len, uint4* __restrict__ packed) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long b = 0;
+    uint32_t iv = 0;
+    for (int j = 0; j < len; ++j) {
+        const int c = codes[(size_t)q * len + j];
+        if (c >= 4) iv |= 1u << j; else b |= (unsigned long long)c << (2 * j);
+    }
+    packed[q] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), iv, 0u);
+}
+
 int launch_build_queries(const char* d_ascii, mg_queries* q, cudaStream_t s) {
     const int total = 2 * q->n * q->len;
     if (total > 0) query_codes_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_ascii, q->n, q->len, q->d_codes);
@@ -71,6 +84,7 @@ int launch_build_queries(const char* d_ascii, mg_queries* q, cudaStream_t s) {
     if (words > 0) query_table_kernel<<<(words + 255) / 256, 256, 0, s>>>(q->d_codes, 2 * q->n, q->len, q->n_groups, q->d_tab);
     const int words2 = q->n_groups * (16 * ((q->len + 1) / 2) + 1);
     if (words2 > 0) query_pair_table_kernel<<<(words2 + 255) / 256, 256, 0, s>>>(q->d_tab, q->len, q->n_groups, q->d_tab2);
+    if (q->n > 0) query_pack_kernel<<<(2 * q->n + 255) / 256, 256, 0, s>>>(q->d_codes, 2 * q->n, q->len, q->d_packed);
     MG_CUDA(cudaGetLastError());
     return MG_OK;
 }
@@ -99,6 +113,7 @@ int mg_queries_create(const char* grna, int n, int len, void* stream, mg_queries
     MG_CUDA(cudaMalloc(&q->d_codes, 2 * nbytes + 16));
     MG_CUDA(cudaMalloc(&q->d_tab, ((size_t)q->n_groups * (4 * len + 1) + 4) * 4));
     MG_CUDA(cudaMalloc(&q->d_tab2, ((size_t)q->n_groups * (16 * ((len + 1) / 2) + 1) + 4) * 4));
+    MG_CUDA(cudaMalloc(&q->d_packed, sizeof(uint4) * ((size_t)2 * n + 1)));
     if (nbytes) MG_CUDA(cudaMemcpyAsync(d_ascii, grna, nbytes, cudaMemcpyHostToDevice, s));
     int rc = launch_build_queries(d_ascii, q, s);
     MG_CUDA(cudaStreamSynchronize(s));
@@ -113,7 +128,7 @@ int mg_queries_length(const mg_queries* q) { return q ? q->len : 0; }
 
 void mg_queries_free(mg_queries* q) {
     if (!q) return;
-    cudaFree(q->d_codes); cudaFree(q->d_tab); cudaFree(q->d_tab2);
+    cudaFree(q->d_codes); cudaFree(q->d_tab); cudaFree(q->d_tab2); cudaFree(q->d_packed);
     delete q;
 }
 

@@ -15,8 +15,8 @@ namespace mg {
 
 int launch_screen_bitsliced_general(const mg_genome* g, const mg_queries* q, int k, const GeneralCtx* d_ctx,
                                     int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s);
-int launch_gapped_rows(const mg_genome* g, const mg_queries* q, const GeneralCtx* d_ctx, int K, int strand, int64_t eb,
-                       int64_t ee, uint32_t** d_tab5_cache, cudaStream_t s);
+int launch_gapped_rows(const mg_genome* g, const mg_queries* q, const GeneralCtx* d_ctx, int K, int strand, int g_begin,
+                       int g_end, int64_t eb, int64_t ee, uint32_t** d_tab_cache, cudaStream_t s);
 
 // ----------------------------------------------------------------------------------------- Myers <= K
 constexpr int kMyersThreads = 128;     // gRNA per CTA (one per thread; a warp shares the text character)
@@ -147,7 +147,7 @@ verify_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx,
     if (i >= n_cand) return;
     const Cand c = ctx->cand[i];
     const int gi = c.q < qv.n ? c.q : c.q - qv.n;
-    if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * qv.len, c.q < qv.n ? 1 : -1, c.e)) atomicAdd(counts + c.q, 1u);
+    if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * qv.len, qv.packed + gi, c.q < qv.n ? 1 : -1, c.e)) atomicAdd(counts + c.q, 1u);
 }
 
 // ----------------------------------------------------------------------------------------- every cell
@@ -160,7 +160,7 @@ allcells_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ct
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = eb + idx % n_anchor;
         const int gi = (int)(idx / n_anchor);
-        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, strand, e))
+        if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * L, qv.packed + gi, strand, e))
             atomicAdd(counts + (strand > 0 ? gi : N + gi), 1u);
     }
 }
@@ -247,7 +247,11 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     uint32_t* d_tab5 = nullptr;                                   // tables of the bit-sliced edit-distance kernel
     const char* gapped_env = getenv("MG_GAPPED_PREFILTER");       // "myers": the one-pattern-per-thread kernel (A/B)
     const bool use_rows = !(gapped_env && strcmp(gapped_env, "myers") == 0);
-    auto prefilter = [&](int64_t a, int64_t b) -> int {
+    // Only the edit-distance rows kernel can also be cut by gRNA group [g0, g1) (groups of 32 gRNA): its threads own
+    // long runs of text, so cutting the text would multiply the L+K warm-up characters every run starts with.
+    const bool group_slices = by_myers && use_rows;
+    const int n_query_groups = group_slices ? (q->n + 31) / 32 : 1;
+    auto prefilter = [&](int64_t a, int64_t b, int g0, int g1) -> int {
         if (by_pieces) {
             const int S = 4 * L + 1;
             const int max_groups = (smem_max - 1024) / (S * 4);
@@ -266,7 +270,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             const int64_t n_anchor = ee - eb;
             if (n_anchor <= 0) continue;
             if (by_myers && use_rows) {
-                const int r2 = launch_gapped_rows(g, q, d_ctx, K, strand, eb, ee, &d_tab5, s);
+                const int r2 = launch_gapped_rows(g, q, d_ctx, K, strand, g0, g1, eb, ee, &d_tab5, s);
                 if (r2 != MG_OK) return r2;
             } else if (by_myers) {
                 dim3 grid((unsigned)((n_anchor + kMyersChunk - 1) / kMyersChunk), (unsigned)((q->n + kMyersThreads - 1) / kMyersThreads), 1);
@@ -280,53 +284,59 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         return MG_OK;
     };
 
-    // Run [wb, we) in slices whose survivors fit the queue; an overflowing slice is re-run in as many parts as
-    // its survivor count calls for (nothing of it has been verified yet, so no double counting).
-    std::vector<std::pair<int64_t, int64_t>> todo;
+    // Run [wb, we) x [all gRNA groups) in slices whose survivors fit the queue; an overflowing slice is re-run in as
+    // many parts as its survivor count calls for (nothing of it has been verified yet, so no double counting).
+    struct Slice { int64_t a, b; int g0, g1; };
+    auto cut = [&](const Slice& r, int64_t parts, std::vector<Slice>& out) {      // pushes the parts in reverse order
+        const int64_t ng = r.g1 - r.g0, len = r.b - r.a;
+        const int64_t gparts = parts < ng ? parts : ng;                           // groups first, then text
+        int64_t tparts = (parts + gparts - 1) / gparts;
+        if (tparts > len) tparts = len;
+        for (int64_t i = gparts - 1; i >= 0; --i)
+            for (int64_t j = tparts - 1; j >= 0; --j)
+                out.push_back(Slice{r.a + len * j / tparts, r.a + len * (j + 1) / tparts,
+                                    (int)(r.g0 + ng * i / gparts), (int)(r.g0 + ng * (i + 1) / gparts)});
+    };
+    std::vector<Slice> todo;
     {   // a small probe slice first: its survivor density sizes the remaining slices, so that an overflow (a wasted
         // prefilter pass) only happens when the density is very uneven
         const int64_t len = we - wb, probe = len / 64;
         int64_t probe_min = 1 << 16;
         if (const char* pm = getenv("MG_PROBE_MIN")) probe_min = atoll(pm) > 0 ? atoll(pm) : probe_min;
-        if (probe >= probe_min) { todo.emplace_back(wb + probe, we); todo.emplace_back(wb, wb + probe); }
-        else todo.emplace_back(wb, we);
+        if (probe >= probe_min) { todo.push_back(Slice{wb + probe, we, 0, n_query_groups}); todo.push_back(Slice{wb, wb + probe, 0, n_query_groups}); }
+        else todo.push_back(Slice{wb, we, 0, n_query_groups});
     }
     bool planned = todo.size() < 2;
     unsigned long long total_cand = 0;
+    int n_slices = 0;
     while (!todo.empty() && rc == MG_OK) {
-        const std::pair<int64_t, int64_t> r = todo.back();
+        const Slice r = todo.back();
         todo.pop_back();
-        if (r.second <= r.first) continue;
+        if (r.b <= r.a || r.g1 <= r.g0) continue;
         MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
-        rc = prefilter(r.first, r.second);
+        rc = prefilter(r.a, r.b, r.g0, r.g1);
         if (rc != MG_OK) break;
+        ++n_slices;
         unsigned long long n_cand = 0;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(&n_cand, h.cand_count, 8, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) break;
         if (n_cand > h.cand_cap) {
-            const int64_t len = r.second - r.first;
-            if (len <= 1) { set_error("candidate queue too small for a single window (%llu survivors)", n_cand); rc = MG_ERR_NOMEM; break; }
+            if (r.b - r.a <= 1 && r.g1 - r.g0 <= 1) { set_error("candidate queue too small for a single window (%llu survivors)", n_cand); rc = MG_ERR_NOMEM; break; }
             int64_t parts = (int64_t)((n_cand + h.cand_cap / 2 - 1) / (h.cand_cap / 2));
-            if (parts > len) parts = len;
             if (parts < 2) parts = 2;
-            for (int64_t i = parts - 1; i >= 0; --i)
-                todo.emplace_back(r.first + len * i / parts, r.first + len * (i + 1) / parts);
+            cut(r, parts, todo);
             continue;
         }
         total_cand += n_cand;
         if (!planned) {          // just finished the probe: cut the rest into slices of ~cap/3 expected survivors
             planned = true;
-            const std::pair<int64_t, int64_t> rest = todo.back();
+            const Slice rest = todo.back();
             todo.pop_back();
-            const double density = (double)n_cand / (double)(r.second - r.first);
-            const double expect = density * (double)(rest.second - rest.first);
-            int64_t parts = (int64_t)(expect / ((double)h.cand_cap / 3.0)) + 1;
-            const int64_t len = rest.second - rest.first;
-            if (parts > len) parts = len;
-            for (int64_t i = parts - 1; i >= 0; --i)
-                todo.emplace_back(rest.first + len * i / parts, rest.first + len * (i + 1) / parts);
+            const double density = (double)n_cand / (double)(r.b - r.a);
+            const double expect = density * (double)(rest.b - rest.a);
+            cut(rest, (int64_t)(expect / ((double)h.cand_cap / 3.0)) + 1, todo);
         }
         if (n_cand > 0) {
             verify_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, s>>>(g->view(), q->view(), d_ctx, n_cand, d_counts);
@@ -335,8 +345,8 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // d_ctx and the queue must outlive the kernels
-    if (getenv("MG_TRACE")) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu\n",
-                                    by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? (use_rows ? "edit-rows" : "myers") : "all-cells", K, total_cand);
+    if (getenv("MG_TRACE")) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu slices=%d\n",
+                                    by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? (use_rows ? "edit-rows" : "myers") : "all-cells", K, total_cand, n_slices);
     dev_free(d_tab5, s);
     dev_free(h.cand, s);
     dev_free(h.cand_count, s);

@@ -220,51 +220,154 @@ __device__ inline uint32_t bit_range(int a, int b) {      // bits [a, b), 0 <= a
     return hi & ~lo;
 }
 
+// even bits of x (bit 2i -> bit i)
+__device__ __forceinline__ uint32_t compress_even(uint32_t lo, uint32_t hi) {
+    auto half = [](uint32_t v) {
+        v &= 0x55555555u;
+        v = (v | (v >> 1)) & 0x33333333u;
+        v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+        v = (v | (v >> 4)) & 0x00FF00FFu;
+        return (v | (v >> 8)) & 0x0000FFFFu;
+    };
+    return half(lo) | (half(hi) << 16);
+}
+
+// Mismatch / off-contig masks of the three diagonals a one-gap alignment ending at e can use, from ONE 32-base window
+// of the strand's text (x0 = e-L-1 .. x0+31) and the packed query: bit j of m0 / mM / mP = query position j against
+// subject e-L+j / e-L+j-1 / e-L+j+1 mismatches (invalid or off-contig bases mismatch), f* = that subject base is off
+// the contig.  Needs L <= 30 and the window inside the buffers; the caller falls back to per-base fetches otherwise.
+__device__ __forceinline__ void diagonal_masks_packed(const GenomeView& gv, int strand, int64_t x0, int L, int64_t cs, int64_t ce,
+                                                      const uint4 qp, uint32_t& m0, uint32_t& mM, uint32_t& mP,
+                                                      uint32_t& f0, uint32_t& fM, uint32_t& fP) {
+    const int n = L + 2;
+    uint32_t lo, hi, inv;
+    if (strand > 0) {
+        load_window(gv, x0, lo, hi, inv);
+    } else {
+        // strand position x0+i is forward base glen-1-x0-i: load the forward window that ENDS there and reverse it
+        uint32_t flo, fhi, finv;
+        load_window(gv, gv.glen - x0 - 32, flo, fhi, finv);
+        auto rev2 = [](uint32_t v) { v = __brev(v); return ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); };
+        lo = ~rev2(fhi);
+        hi = ~rev2(flo);
+        inv = __brev(finv);
+    }
+    // window index i <-> strand position x0 + i; off-contig part of the window
+    const int64_t a = cs - x0, b = ce - x0;
+    const uint32_t on = bit_range((int)max((int64_t)0, min((int64_t)32, a)), (int)max((int64_t)0, min((int64_t)32, b)));
+    const uint32_t off = ~on;
+    const uint32_t all = bit_range(0, L);
+    const uint32_t bad = inv | off;                        // window positions that mismatch everything
+    const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+    const unsigned long long q = ((unsigned long long)qp.y << 32) | qp.x;
+    auto diag = [&](int o) {                               // query position j against window index j + o
+        const unsigned long long x = (w >> (2 * o)) ^ q;
+        const unsigned long long d = x | (x >> 1);
+        return (compress_even((uint32_t)d, (uint32_t)(d >> 32)) | (bad >> o) | qp.z) & all;
+    };
+    mM = diag(0); m0 = diag(1); mP = diag(2);
+    fM = off & all; f0 = (off >> 1) & all; fP = (off >> 2) & all;
+    (void)n;
+}
+
 __device__ inline bool verify_nopattern_one_gap(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
-                                                int strand, int64_t e, int64_t cs, int64_t ce) {
+                                                const uint4* __restrict__ qpacked, int strand, int64_t e, int64_t cs, int64_t ce) {
     const int L = c.L;
     const int64_t base = e - L;                            // D0: query position j <-> subject base + j
     uint32_t m0 = 0, mM = 0, mP = 0, f0 = 0, fM = 0, fP = 0;   // mismatch / off-contig masks per diagonal
-    int prev = -1, cur = -1, next = -1;
-    {
-        const int64_t x0 = base - 1, x1 = base;
-        prev = (x0 >= cs && x0 < ce) ? tbase(gv, strand, x0) : -1;
-        cur = (x1 >= cs && x1 < ce) ? tbase(gv, strand, x1) : -1;
+    const int64_t x0 = base - 1;
+    const int64_t fwd0 = strand > 0 ? x0 : gv.glen - x0 - 32;   // first forward base of the 32-base window
+    if (qpacked != nullptr && L <= 30 && fwd0 >= 0 && fwd0 + 32 <= gv.glen) {
+        diagonal_masks_packed(gv, strand, x0, L, cs, ce, *qpacked, m0, mM, mP, f0, fM, fP);
+    } else {
+        int prev = -1, cur = -1, next = -1;
+        {
+            const int64_t x1 = base;
+            prev = (x0 >= cs && x0 < ce) ? tbase(gv, strand, x0) : -1;
+            cur = (x1 >= cs && x1 < ce) ? tbase(gv, strand, x1) : -1;
+        }
+        for (int j = 0; j < L; ++j) {
+            const int64_t x2 = base + j + 1;
+            next = (x2 >= cs && x2 < ce) ? tbase(gv, strand, x2) : -1;
+            const int qb = q[j];
+            const uint32_t b = 1u << j;
+            if (cur < 0) f0 |= b;
+            if (prev < 0) fM |= b;
+            if (next < 0) fP |= b;
+            if (qb >= 4 || qb != cur) m0 |= b;
+            if (qb >= 4 || qb != prev) mM |= b;
+            if (qb >= 4 || qb != next) mP |= b;
+            prev = cur;
+            cur = next;
+        }
     }
-    for (int j = 0; j < L; ++j) {
-        const int64_t x2 = base + j + 1;
-        next = (x2 >= cs && x2 < ce) ? tbase(gv, strand, x2) : -1;
-        const int qb = q[j];
-        const uint32_t b = 1u << j;
-        if (cur < 0) f0 |= b;
-        if (prev < 0) fM |= b;
-        if (next < 0) fP |= b;
-        if (qb >= 4 || qb != cur) m0 |= b;
-        if (qb >= 4 || qb != prev) mM |= b;
-        if (qb >= 4 || qb != next) mP |= b;
-        prev = cur;
-        cur = next;
+    const int M = c.M, Gp = c.Gp, B = M + Gp;
+    {   // Early reject (most prefilter survivors are unit-cost edit-distance hits with 2+ gaps, or ungapped hits with
+        // M+1 mismatches in the middle).  Necessary conditions, ignoring contig edges, masks and PAM:
+        //  - without a gap some trim [qs,qe) must have mm <= M and mm + u <= B;
+        //  - with one gap, trimming a position adds 1 to u and removes at most 1 mismatch, so every trim costs at least
+        //    the full-length alignment through the same gap position k: 1 + mm_full(k) <= B (which implies mm <= M).
+        bool feasible = false;
+        for (int qe = L; qe >= 1 && L - qe <= B && !feasible; --qe)
+            for (int qs = 0; qs < qe && L - qe + qs <= B; ++qs) {
+                const int mm = __popc(m0 & bit_range(qs, qe));
+                if (mm <= M && mm + L - qe + qs <= B) { feasible = true; break; }
+            }
+        if (!feasible && Gp >= 1) {
+            // del(k) = popc(mM & [0,k)) + popc(m0 & [k,L));  ins(k) = popc(mP & [0,k)) + popc(m0 & [k+1,L));  k = 1..L-1
+            int del = (int)(mM & 1u) + __popc(m0 & bit_range(1, L));
+            int ins = (int)(mP & 1u) + __popc(m0 & bit_range(2, L));
+            int best = min(del, ins);
+            for (int k = 1; k < L - 1; ++k) {
+                del += (int)((mM >> k) & 1u) - (int)((m0 >> k) & 1u);
+                ins += (int)((mP >> k) & 1u) - (int)((m0 >> (k + 1)) & 1u);
+                best = min(best, min(del, ins));
+            }
+            feasible = 1 + best <= B;
+        }
+        if (!feasible) return false;
     }
-    const int B = c.M + c.Gp;
+    const bool edge = (f0 | fM | fP) != 0u;                // some base of the three diagonals is off the contig
     for (int qe = L; qe >= 1 && L - qe <= B; --qe) {
         const int trim3 = L - qe;
         for (int qs = 0; qs < qe && trim3 + qs <= B; ++qs) {          // no gap
             const uint32_t r = bit_range(qs, qe);
             if (f0 & r) continue;
             const int mm = __popc(m0 & r);
-            if (mm > c.M || mm + trim3 + qs > B) continue;
+            if (mm > M || mm + trim3 + qs > B) continue;
             const AlnState a{m0 & r, 0u, 0u, 0u, mm, 0};
             if (alignment_problematic(gv, c, strand, a, qs, qe, base + qs, base + qe, cs, ce)) return true;
         }
-        if (c.Gp < 1) continue;
+        if (Gp < 1) continue;
         for (int qs = 0; qs < qe && trim3 + qs + 1 <= B; ++qs) {
             const int u = trim3 + qs;
+            const int T = min(M, B - 1 - u);                            // most mismatches a one-gap alignment may have here
+            if (!edge) {
+                // the mismatch count moves by one bit of each diagonal per step of the gap position
+                int mm = (int)((mM >> qs) & 1u) + __popc(m0 & bit_range(qs + 1, qe));
+                for (int k = qs + 1; k <= qe - 1; ++k) {                // deletion before query position k
+                    if (mm <= T) {
+                        const AlnState a{(mM & bit_range(qs, k)) | (m0 & bit_range(k, qe)), 0u, 1u << k, 0u, mm, 1};
+                        if (alignment_problematic(gv, c, strand, a, qs, qe, base - 1 + qs, base + qe, cs, ce)) return true;
+                    }
+                    mm += (int)((mM >> k) & 1u) - (int)((m0 >> k) & 1u);
+                }
+                mm = (int)((mP >> qs) & 1u) + __popc(m0 & bit_range(qs + 2, qe));
+                for (int k = qs + 1; k <= qe - 2; ++k) {                // insertion at query position k
+                    if (mm <= T) {
+                        const AlnState a{(mP & bit_range(qs, k)) | (m0 & bit_range(k + 1, qe)), 1u << k, 0u, 0u, mm, 1};
+                        if (alignment_problematic(gv, c, strand, a, qs, qe, base + 1 + qs, base + qe, cs, ce)) return true;
+                    }
+                    mm += (int)((mP >> k) & 1u) - (int)((m0 >> (k + 1)) & 1u);
+                }
+                continue;
+            }
             for (int k = qs + 1; k <= qe - 1; ++k) {                    // deletion before query position k
                 const uint32_t rp = bit_range(qs, k), rs = bit_range(k, qe);
                 if ((fM & rp) | (f0 & rs)) continue;
                 const uint32_t mb = (mM & rp) | (m0 & rs);
                 const int mm = __popc(mb);
-                if (mm > c.M || mm + 1 + u > B) continue;
+                if (mm > T) continue;
                 const AlnState a{mb, 0u, 1u << k, 0u, mm, 1};
                 if (alignment_problematic(gv, c, strand, a, qs, qe, base - 1 + qs, base + qe, cs, ce)) return true;
             }
@@ -273,7 +376,7 @@ __device__ inline bool verify_nopattern_one_gap(const GenomeView& gv, const Gene
                 if ((fP & rp) | (f0 & rs)) continue;
                 const uint32_t mb = (mP & rp) | (m0 & rs);
                 const int mm = __popc(mb);
-                if (mm > c.M || mm + 1 + u > B) continue;
+                if (mm > T) continue;
                 const AlnState a{mb, 1u << k, 0u, 0u, mm, 1};
                 if (alignment_problematic(gv, c, strand, a, qs, qe, base + 1 + qs, base + qe, cs, ce)) return true;
             }
@@ -294,7 +397,7 @@ struct Frame {
 
 // gRNA `q` (codes in gRNA orientation, 5'->3'), strand, virtual end e in strand coordinates.
 static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
-                                           int strand, int64_t e) {
+                                           const uint4* __restrict__ qpacked, int strand, int64_t e) {
     const int L = c.L;
     // the contig (strand coordinates) that intersects [e - L - Gp, e)
     const int64_t lo = e - L - c.Gp, hi = e;
@@ -308,7 +411,7 @@ static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const Ge
     const int64_t cs = strand > 0 ? gv.cstart[ci] : gv.glen - gv.cend[ci];
     const int64_t ce = strand > 0 ? gv.cend[ci] : gv.glen - gv.cstart[ci];
 
-    if (c.n_units == 0 && c.Gp <= 1) return verify_nopattern_one_gap(gv, c, q, strand, e, cs, ce);
+    if (c.n_units == 0 && c.Gp <= 1) return verify_nopattern_one_gap(gv, c, q, qpacked, strand, e, cs, ce);
 
     Frame st[kMaxDepth];
     for (int qe = L; qe >= 1; --qe) {

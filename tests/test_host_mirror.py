@@ -307,3 +307,54 @@ def test_generated_threshold_networks_exhaustively():
         assert result == want, (T, K)
         checked += 1
     assert checked >= 60
+
+
+def test_edit_distance_rows_arithmetic_identities():
+    """The gapped prefilter (csrc/screen_gapped.cu) computes two of Hyyro's five per-cell words as carry-free integer
+    arithmetic (IMAD on the FMA pipe) instead of LOP3.  Check, on whole 32-bit words and over every reachable per-bit
+    state, that the arithmetic column update equals the boolean one and that both equal the plain edit-distance DP."""
+    import numpy as np
+    M32 = 0xFFFFFFFF
+    rng = np.random.default_rng(5)
+    L, n_chars = 9, 400
+    pattern = rng.integers(0, 4, size=(32, L))                   # 32 queries, one per bit
+    text = rng.integers(0, 5, size=n_chars)                      # 4 = invalid base (mismatches everything)
+    Pv = [M32] * L; Mv = [0] * L                                 # boolean formulation
+    Pa = [M32] * L; Ma = [0] * L; X = [1] * L                    # arithmetic formulation: X = Mv - Pv (mod 2^32)
+    col = np.tile(np.arange(1, L + 1), (32, 1))                  # plain DP column D[1..L][j] per query
+    for c in text:
+        mis = [sum(1 << k for k in range(32) if c == 4 or pattern[k, i] != c) for i in range(L)]
+        Ph = Mh = 0
+        Pha = Mha = Dh = 0
+        for i in range(L):
+            nD0 = mis[i] & ~Mv[i] & ~Mh & M32
+            Mh_out = Pv[i] & ~nD0 & M32
+            Ph_out = (Mv[i] | (nD0 & ~Pv[i])) & M32
+            Pv_new = (Mh | (nD0 & ~Ph)) & M32
+            Mv_new = Ph & ~nD0 & M32
+            Pv[i], Mv[i], Ph, Mh = Pv_new, Mv_new, Ph_out, Mh_out
+            nD0a = mis[i] & ~Ma[i] & ~Mha & M32
+            Mha_out = Pa[i] & ~nD0a & M32
+            Ma_new = Pha & ~nD0a & M32
+            Dh_out = (nD0a + X[i]) & M32
+            Pha_out = (Mha_out + Dh_out) & M32
+            X[i] = (Dh - nD0a) & M32
+            Pa[i] = (Ma_new - X[i]) & M32
+            Ma[i] = Ma_new
+            Dh, Pha, Mha = Dh_out, Pha_out, Mha_out
+            assert (Pa[i], Ma[i], Pha, Mha) == (Pv[i], Mv[i], Ph, Mh)
+            assert X[i] == (Ma[i] - Pa[i]) & M32 and Dh == (Pha - Mha) & M32
+            assert Pv[i] & Mv[i] == 0 and Ph & Mh == 0
+        new = np.empty_like(col)                                  # reference DP, D[0][j] = 0
+        for k in range(32):
+            up_left, up = 0, 0
+            for i in range(L):
+                cost = 0 if (c != 4 and pattern[k, i] == c) else 1
+                v = min(up_left + cost, up + 1, col[k, i] + 1)
+                up_left, up = col[k, i], v
+                new[k, i] = v
+        for i in range(L):                                        # vertical deltas of the new column
+            for k in range(32):
+                d = new[k, i] - (new[k, i - 1] if i else 0)
+                assert ((Pv[i] >> k) & 1, (Mv[i] >> k) & 1) == (int(d == 1), int(d == -1))
+        col = new

@@ -34,10 +34,11 @@ def main():
         ("pattern 0mg-10,1mg-11- with <=1 gap (config 3)", 135e6, 10000, 20, dict(ot_pattern="0mg-10,1mg-11-", ot_gap=2), ".NGG"),
     ]
     only = sys.argv[1:]
+    scale = float(os.environ.get("MG_BENCH_SCALE", "1"))          # genome size factor (profiling under ncu)
     for name, nb, n, L, kw, pam in cases:
         if only and not any(o in name for o in only):
             continue
-        nb = int(nb)
+        nb = int(nb * scale)
         codes = torch.randint(0, 4, (nb,), dtype=torch.uint8, device=dev, generator=gen)
         ascii_ = torch.take(lut, codes.to(torch.int64))
         del codes
