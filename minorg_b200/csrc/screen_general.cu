@@ -74,69 +74,150 @@ myers_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, 
 // ----------------------------------------------------------------------------------------- exact pieces
 // Pigeonhole prefilter for patterns (host proof: ot_regex.OffTargetExpression.exact_pieces): a query survives at
 // window p iff it matches the subject exactly on one of the given position ranges.  Same bit-sliced tables as
-// the scan kernel (OR of the mismatch words of a range == 0).  A gap after (before) the matching range moves
-// the alignment's virtual end by at most Gp, so 2*Gp+1 anchors go to the exact verifier.
-constexpr int kPieceThreads = 512;
+// the scan kernel (OR of the mismatch words of a range == 0): pair words where two positions of the range share
+// one, single-position words at an odd edge.  One launch per (piece, orientation), instantiated for its number of
+// lookups T; after the first three words a thread drops the group unless some query still matches (a 6-base exact
+// match: 1 word in 128), so the kernel runs at ~3.4 shared loads per (window, 32 gRNA).  Four groups per trip and 32
+// warps per SM keep enough loads in flight (one group per trip with 16 warps was latency-bound at half the rate;
+// looking at four words before the drop instead of three measures the same).  A gap after (before) the
+// matching range moves the alignment's virtual end by at most Gp, so 2*Gp+1 anchors go to the exact verifier.
+constexpr int kPieceThreads = 1024;
 constexpr int kPieceMax = 16;          // positions of a piece that are compared (a longer piece is cut: still necessary)
+constexpr int kPieceLookups = 9;       // 16 positions: at most 7 pair words + 2 single words
 
+struct PieceOp {
+    int minus;                         // 1: the reverse-complement queries (mirrored range)
+    int n;                             // lookups
+    int pair[kPieceLookups];           // 1: idx = pair index (positions 2 idx, 2 idx + 1); 0: idx = position
+    int idx[kPieceLookups];
+};
+
+// cold path: the queries of group word `hit` (already restricted to the op's orientation) survive at window p
+static __device__ __noinline__ void emit_piece_hits(const GeneralCtx* __restrict__ ctx, uint32_t hit, int q0, int N, int L,
+                                                    int64_t p, int64_t glen) {
+    const int Gp = ctx->Gp;
+    while (hit) {
+        const int i = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const int q = q0 + i;
+        if (q >= 2 * N) continue;
+        const int64_t e0 = q < N ? p + L : glen - p;
+        for (int d = -Gp; d <= Gp; ++d) emit_candidate(*ctx, q, e0 + d);
+    }
+}
+
+template <int T, int EE>
 __global__ void __launch_bounds__(kPieceThreads, 1)
-pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, int groups_per_chunk, int64_t wb,
-              int64_t we, uint32_t* __restrict__ counts) {
-    extern __shared__ uint32_t tab[];
-    const int L = qv.len, S = 4 * L + 1, N = qv.n;
-    const int n_pieces = ctx->n_pieces, Gp = ctx->Gp;
-    const int g_split = N / 32;            // groups below hold only '+' queries; group g_split may hold both
-    for (int cg = 0; cg < qv.n_groups; cg += groups_per_chunk) {
-        const int ng = min(groups_per_chunk, qv.n_groups - cg);
+pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, PieceOp op, int groups_per_chunk, int64_t wb,
+              int64_t we) {
+    extern __shared__ uint32_t tab[];                      // per group: pair table, then single-position table
+    const int L = qv.len, N = qv.n, NPL = (L + 1) / 2;
+    const int S2 = 16 * NPL + 1, S1 = 4 * L + 1, SG = S2 + S1;
+    constexpr int E = T < EE ? T : EE;                     // words looked at before the early drop
+    // groups holding queries of this orientation: '+' queries are 0..N-1, '-' queries N..2N-1 (group N/32 may hold both)
+    const int g_lo = op.minus ? N / 32 : 0, g_hi = op.minus ? qv.n_groups : (N + 31) / 32;
+    for (int cg = g_lo; cg < g_hi; cg += groups_per_chunk) {
+        const int ng = min(groups_per_chunk, g_hi - cg);
         __syncthreads();
-        for (int i = threadIdx.x; i < ng * S; i += blockDim.x) tab[i] = __ldg(qv.tab + (size_t)cg * S + i);
+        for (int i = threadIdx.x; i < ng * SG; i += blockDim.x) {
+            const int g = i / SG, r = i - g * SG;
+            tab[i] = r < S2 ? __ldg(qv.tab2 + (size_t)(cg + g) * S2 + r) : __ldg(qv.tab + (size_t)(cg + g) * S1 + (r - S2));
+        }
         __syncthreads();
         for (int64_t p = wb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < we; p += (int64_t)gridDim.x * blockDim.x) {
             uint32_t lo, hi, inv;
             load_window(gv, p, lo, hi, inv);
             const unsigned long long w = ((unsigned long long)hi << 32) | lo;
-            for (int op = 0; op < 2 * n_pieces; ++op) {
-                // oriented piece: '+' queries compare gRNA positions [a, a+n), '-' queries the mirrored range
-                const int k = op >> 1;
-                const bool minus = op & 1;
-                const uint32_t m = minus ? ctx->piece_rev[k] : ctx->piece_fwd[k];
-                const int a = __ffs(m) - 1;
-                const int n = min(__popc(m), kPieceMax);
-                uint32_t off[kPieceMax];                   // byte offsets of the table words of this window
+            uint32_t off[T];                               // byte offsets of this window's table words inside a group
 #pragma unroll
-                for (int x = 0; x < kPieceMax; ++x) {
-                    const int j = min(a + x, L - 1);
-                    const uint32_t code = (uint32_t)(w >> (2 * j)) & 3u;
-                    off[x] = (((inv >> j) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * j) + code) * 4u;
+            for (int x = 0; x < T; ++x) {
+                const int k = op.idx[x];
+                uint32_t word;
+                if (op.pair[x]) {
+                    const uint32_t nib = (uint32_t)(w >> (4 * k)) & 15u;
+                    word = ((inv >> (2 * k)) & 3u) ? (uint32_t)(16 * NPL) : (uint32_t)(16 * k) + nib;
+                } else {
+                    const uint32_t code = (uint32_t)(w >> (2 * k)) & 3u;
+                    word = (uint32_t)S2 + (((inv >> k) & 1u) ? (uint32_t)(4 * L) : (uint32_t)(4 * k) + code);
                 }
-                // groups of this orientation inside the resident chunk
-                int g_lo = minus ? max(g_split, cg) : cg;
-                int g_hi = minus ? cg + ng : min(cg + ng, (N + 31) / 32);
-                for (int g = g_lo; g < g_hi; ++g) {
-                    const char* t = reinterpret_cast<const char*>(tab + (size_t)(g - cg) * S);
-                    uint32_t acc = 0u;
+                off[x] = word * 4u;
+            }
+            // the rest of the words of one group and, for the (rare) survivors, the hand-over to the verifier
+            auto finish = [&](int g, const char* t, uint32_t acc) {
 #pragma unroll
-                    for (int x = 0; x < kPieceMax; ++x)
-                        if (x < n) acc |= *reinterpret_cast<const uint32_t*>(t + off[x]);
-                    uint32_t hit = ~acc;
-                    if (hit == 0u) continue;
-                    const int q0 = g * 32;
-                    uint32_t plus_bits = 0u;
-                    if (q0 + 32 <= N) plus_bits = 0xFFFFFFFFu;
-                    else if (q0 < N) plus_bits = (1u << (N - q0)) - 1u;
-                    hit &= minus ? ~plus_bits : plus_bits;
-                    while (hit) {
-                        const int i = __ffs(hit) - 1;
-                        hit &= hit - 1;
-                        const int q = q0 + i;
-                        if (q >= 2 * N) continue;
-                        const int64_t e0 = q < N ? p + L : gv.glen - p;
-                        for (int d = -Gp; d <= Gp; ++d) emit_candidate(*ctx, q, e0 + d);
-                    }
+                for (int x = E; x < T; ++x) acc |= *reinterpret_cast<const uint32_t*>(t + off[x]);
+                uint32_t hit = ~acc;
+                if (hit == 0u) return;
+                const int q0 = (cg + g) * 32;
+                uint32_t plus_bits = 0u;
+                if (q0 + 32 <= N) plus_bits = 0xFFFFFFFFu;
+                else if (q0 < N) plus_bits = (1u << (N - q0)) - 1u;
+                hit &= op.minus ? ~plus_bits : plus_bits;
+                if (hit) emit_piece_hits(ctx, hit, q0, N, L, p, gv.glen);
+            };
+            const char* t = reinterpret_cast<const char*>(tab);
+            int g = 0;
+            // U groups per trip so that their loads are in flight together: one group per trip is latency-bound
+            // (load -> OR -> compare -> branch with 4 warps per scheduler: issue slots 48 % busy, ncu)
+            constexpr int U = 4;
+            for (; g + U <= ng; g += U, t += U * SG * 4) {
+                uint32_t acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    acc[u] = 0u;
+#pragma unroll
+                    for (int x = 0; x < E; ++x) acc[u] |= *reinterpret_cast<const uint32_t*>(t + u * (SG * 4) + off[x]);
                 }
+                uint32_t all = acc[0];
+#pragma unroll
+                for (int u = 1; u < U; ++u) all &= acc[u];
+                if (all == 0xFFFFFFFFu) continue;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (acc[u] != 0xFFFFFFFFu) finish(g + u, t + u * (SG * 4), acc[u]);
+            }
+            for (; g < ng; ++g, t += SG * 4) {
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int x = 0; x < E; ++x) acc |= *reinterpret_cast<const uint32_t*>(t + off[x]);
+                if (acc != 0xFFFFFFFFu) finish(g, t, acc);
             }
         }
     }
+}
+
+// the lookups that cover query positions [a, a + n) (of the orientation's own coordinates)
+static PieceOp make_piece_op(int a, int n, int minus) {
+    PieceOp op;
+    memset(&op, 0, sizeof op);
+    op.minus = minus;
+    if (n > kPieceMax) n = kPieceMax;
+    for (int j = a; j < a + n && op.n < kPieceLookups;) {
+        if (j % 2 == 0 && j + 1 < a + n) { op.pair[op.n] = 1; op.idx[op.n] = j / 2; j += 2; }
+        else { op.pair[op.n] = 0; op.idx[op.n] = j; j += 1; }
+        ++op.n;
+    }
+    return op;
+}
+
+static int launch_pieces(const mg_genome* g, const mg_queries* q, const GeneralCtx* d_ctx, const PieceOp& op, int sms, int smem_max,
+                         int64_t a, int64_t b, cudaStream_t s) {
+    const int L = q->len, SG = 16 * ((L + 1) / 2) + 1 + 4 * L + 1;
+    const int max_groups = (smem_max - 1024) / (SG * 4);
+    const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
+    const size_t smem = (size_t)gpc * SG * 4;
+    int64_t grid = (b - a + kPieceThreads - 1) / kPieceThreads;
+    if (grid > sms) grid = sms;
+    switch (op.n) {
+#define MG_PIECES(TT) case TT: \
+        MG_CUDA(cudaFuncSetAttribute(pieces_kernel<TT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pieces_kernel<TT, 3><<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, op, gpc, a, b); break;
+        MG_PIECES(1) MG_PIECES(2) MG_PIECES(3) MG_PIECES(4) MG_PIECES(5) MG_PIECES(6) MG_PIECES(7) MG_PIECES(8) MG_PIECES(9)
+#undef MG_PIECES
+        default: set_error("piece with %d lookups", op.n); return MG_ERR_ARG;
+    }
+    MG_CUDA(cudaGetLastError());
+    return MG_OK;
 }
 
 // ----------------------------------------------------------------------------------------- verifier pass
@@ -253,14 +334,13 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     const int n_query_groups = group_slices ? (q->n + 31) / 32 : 1;
     auto prefilter = [&](int64_t a, int64_t b, int g0, int g1) -> int {
         if (by_pieces) {
-            const int S = 4 * L + 1;
-            const int max_groups = (smem_max - 1024) / (S * 4);
-            const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
-            const size_t smem = (size_t)gpc * S * 4;
-            cudaFuncSetAttribute(pieces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int64_t grid = (b - a + kPieceThreads - 1) / kPieceThreads;
-            if (grid > sms) grid = sms;
-            pieces_kernel<<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, gpc, a, b, d_counts);
+            for (int k = 0; k < h.n_pieces; ++k)
+                for (int minus = 0; minus < 2; ++minus) {
+                    const int pa = crit->piece_start[k], pn = crit->piece_len[k];
+                    const PieceOp op = make_piece_op(minus ? L - pa - pn : pa, pn, minus);
+                    const int r2 = launch_pieces(g, q, d_ctx, op, sms, smem_max, a, b, s);
+                    if (r2 != MG_OK) return r2;
+                }
             return MG_OK;
         }
         if (by_hamming) return launch_screen_bitsliced_general(g, q, K, d_ctx, a, b, d_counts, s);
