@@ -203,11 +203,14 @@ static int launch_rows(const mg_genome* g, const mg_queries* q, const uint32_t* 
     auto kern = alu_only ? gapped_rows_kernel<L, 0> : gapped_rows_kernel<L, L>;
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_anchor = ee - eb;
-    // characters per thread: long enough to amortise the L+K warm-up, short enough to fill the machine
-    int64_t run = (n_anchor + (int64_t)sms * kRowsThreads - 1) / ((int64_t)sms * kRowsThreads);
+    // characters per thread: long enough to amortise the L+K warm-up, short enough to fill the machine; whole waves of
+    // CTAs (one CTA per SM), and a multiple of 16 so that every lane of a warp sits at the same offset inside its
+    // 16-character block
+    const int64_t per_wave = (int64_t)sms * kRowsThreads;
+    const int64_t waves = (n_anchor + per_wave * 4096 - 1) / (per_wave * 4096);
+    int64_t run = (n_anchor + per_wave * waves - 1) / (per_wave * waves);
     if (run < 64) run = 64;
-    if (run > 4096) run = 4096;
-    run = (run + 15) / 16 * 16;          // every lane of a warp then sits at the same offset inside its 16-character block
+    run = (run + 15) / 16 * 16;
     const int64_t threads = (n_anchor + run - 1) / run;
     const unsigned grid = (unsigned)((threads + kRowsThreads - 1) / kRowsThreads);
     kern<<<grid, kRowsThreads, smem, s>>>(g->view(), q->view(), d_tab, d_ctx, K, strand, gpc, g_begin, g_end, eb, ee, (int)run,

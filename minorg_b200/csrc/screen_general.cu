@@ -8,6 +8,7 @@
 //   verifier   verify.cuh: exact enumeration of the alignment universe at the surviving anchors.
 // K = max_mismatch + max_gap without a pattern (MINORg.py:2037-2038: unaligned positions and gaps spend one
 // combined budget), or the bound the host derives from the pattern (ot_regex.OffTargetExpression.edit_bound).
+#include <chrono>
 #include "common.cuh"
 #include "verify.cuh"
 
@@ -295,7 +296,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         h.piece_rev[k] = r;
     }
     // candidate queue between the prefilter and the verifier pass
-    h.cand_cap = 16ull << 20;
+    h.cand_cap = 64ull << 20;                                   // 1 GB of 16-byte entries
     if (const char* cap_env = getenv("MG_QUEUE_CAP")) {          // tests shrink the queue to exercise the re-cut path
         const long long v = atoll(cap_env);
         if (v >= 8) h.cand_cap = (unsigned long long)v;
@@ -378,22 +379,32 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
                                     (int)(r.g0 + ng * i / gparts), (int)(r.g0 + ng * (i + 1) / gparts)});
     };
     std::vector<Slice> todo;
+    Slice rest{0, 0, 0, 0};
+    bool have_rest = false;
     {   // a small probe slice first: its survivor density sizes the remaining slices, so that an overflow (a wasted
         // prefilter pass) only happens when the density is very uneven
         const int64_t len = we - wb, probe = len / 64;
         int64_t probe_min = 1 << 16;
         if (const char* pm = getenv("MG_PROBE_MIN")) probe_min = atoll(pm) > 0 ? atoll(pm) : probe_min;
-        if (probe >= probe_min) { todo.push_back(Slice{wb + probe, we, 0, n_query_groups}); todo.push_back(Slice{wb, wb + probe, 0, n_query_groups}); }
-        else todo.push_back(Slice{wb, we, 0, n_query_groups});
+        if (probe >= probe_min) {
+            rest = Slice{wb + probe, we, 0, n_query_groups};
+            have_rest = true;
+            todo.push_back(Slice{wb, wb + probe, 0, n_query_groups});
+        } else {
+            todo.push_back(Slice{wb, we, 0, n_query_groups});
+        }
     }
-    bool planned = todo.size() < 2;
     unsigned long long total_cand = 0;
     int n_slices = 0;
+    const bool trace = getenv("MG_TRACE") != nullptr;      // adds a synchronisation per slice to time the two passes
+    double t_prefilter = 0.0, t_verify = 0.0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (!todo.empty() && rc == MG_OK) {
         const Slice r = todo.back();
         todo.pop_back();
         if (r.b <= r.a || r.g1 <= r.g0) continue;
         MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
+        const double t0 = trace ? now() : 0.0;
         rc = prefilter(r.a, r.b, r.g0, r.g1);
         if (rc != MG_OK) break;
         ++n_slices;
@@ -402,6 +413,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         if (e == cudaSuccess) e = cudaMemcpyAsync(&n_cand, h.cand_count, 8, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) break;
+        if (trace) t_prefilter += now() - t0;
         if (n_cand > h.cand_cap) {
             if (r.b - r.a <= 1 && r.g1 - r.g0 <= 1) { set_error("candidate queue too small for a single window (%llu survivors)", n_cand); rc = MG_ERR_NOMEM; break; }
             int64_t parts = (int64_t)((n_cand + h.cand_cap / 2 - 1) / (h.cand_cap / 2));
@@ -410,23 +422,24 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             continue;
         }
         total_cand += n_cand;
-        if (!planned) {          // just finished the probe: cut the rest into slices of ~cap/3 expected survivors
-            planned = true;
-            const Slice rest = todo.back();
-            todo.pop_back();
-            const double density = (double)n_cand / (double)(r.b - r.a);
-            const double expect = density * (double)(rest.b - rest.a);
+        if (have_rest) {         // the first slice that fitted (the probe or, if it overflowed, a part of it): cut the
+            have_rest = false;   // rest into slices of ~cap/3 expected survivors, by its density per (position, group)
+            const double density = (double)n_cand / ((double)(r.b - r.a) * (double)(r.g1 - r.g0));
+            const double expect = density * (double)(rest.b - rest.a) * (double)(rest.g1 - rest.g0);
             cut(rest, (int64_t)(expect / ((double)h.cand_cap / 3.0)) + 1, todo);
         }
         if (n_cand > 0) {
+            const double t1 = trace ? now() : 0.0;
             verify_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, s>>>(g->view(), q->view(), d_ctx, n_cand, d_counts);
             e = cudaGetLastError();
             if (e != cudaSuccess) break;
+            if (trace) { cudaStreamSynchronize(s); t_verify += now() - t1; }
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // d_ctx and the queue must outlive the kernels
-    if (getenv("MG_TRACE")) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu slices=%d\n",
-                                    by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? (use_rows ? "edit-rows" : "myers") : "all-cells", K, total_cand, n_slices);
+    if (trace) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu slices=%d prefilter %.1f ms verify %.1f ms\n",
+                       by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? (use_rows ? "edit-rows" : "myers") : "all-cells", K, total_cand, n_slices,
+                       t_prefilter * 1e3, t_verify * 1e3);
     dev_free(d_tab5, s);
     dev_free(h.cand, s);
     dev_free(h.cand_count, s);
