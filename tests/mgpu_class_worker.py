@@ -18,6 +18,8 @@ def main():
     m = MINORg(directory=os.path.join(out, "rank%d" % rank), prefix="mg", device=local)
     m.target = os.path.join(data, "targets.fasta")
     m.ot_mismatch = 2
+    if mode == "windows_gapped":  # general path (edit-distance prefilter + verifier) over window shards of one genome
+        m.ot_gap = 2
     if mode == "files":          # three subject files over the ranks
         m.reference = {"TAIR10": os.path.join(data, "subset_ref_TAIR10.fasta")}
         m.add_query(os.path.join(data, "subset_9654.fasta"), alias="9654")

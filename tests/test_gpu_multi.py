@@ -26,7 +26,7 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["files", "windows"])
+@pytest.mark.parametrize("mode", ["files", "windows", "windows_gapped"])
 def test_two_ranks_match_oracle(tmp_path, mode):
     d = tmp_path / "data"
     d.mkdir()
@@ -50,6 +50,10 @@ def test_two_ranks_match_oracle(tmp_path, mode):
         contigs = O.read_fasta(str(d / f))
         names = [c[0] for c in contigs]
         masks = [(names.index(c), s, e) for _, c, s, e in O.find_masks(targets, contigs)]
-        fail |= c_oracle.screen_hamming(contigs, masks, seqs, 1, threads=8) > 0
+        if mode == "windows_gapped":        # ot_mismatch=2, ot_gap=2 -> M = 1, Gp = 1
+            c = c_oracle.screen_nopattern(contigs, masks, seqs, 1, 1, threads=16)
+            fail |= (c[:len(seqs)] + c[len(seqs):]) > 0
+        else:
+            fail |= c_oracle.screen_hamming(contigs, masks, seqs, 1, threads=8) > 0
     assert got == [s for s, fl in zip(seqs, fail) if fl]
     assert 0 < len(got) < len(seqs)
