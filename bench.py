@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the gapped / pattern side measurements (N=1 only)")
     return ap.parse_args()
 
 
@@ -312,6 +313,32 @@ def main():
     host_counts = (counts[:n] + counts[n:]).cpu().numpy()
     fails = int((host_counts > 0).sum())
 
+    # ---- side measurements (N=1): the other criteria of the path on the same resident genomes, one timed pass each
+    # after one warm-up pass.  Not the headline: the gapped line is the north star's <=4 mm / <=1 gap criterion.
+    other_modes = None
+    if world == 1 and not args.no_other_modes:
+        other_modes = []
+        for label, n_sub, kw in (("gapped: <=4 mismatches / <=1 gap (edit-distance rows kernel + verifier)", min(n, 2048), dict(ot_mismatch=MAX_MISMATCH + 1, ot_gap=2)),
+                                 ("pattern 0mg-10,1mg-11- with <=1 gap (BASELINE configs[2]; exact-piece kernel + verifier)", n, dict(ot_pattern="0mg-10,1mg-11-", ot_gap=2)),
+                                 ("reference defaults: ot_mismatch=1 (exact off-target copies only)", n, dict(ot_mismatch=1))):
+            q_sub = queries if n_sub == n else _lib.Queries(grnas[:n_sub], stream=stream)
+            c_sub = torch.zeros(2 * n_sub, dtype=torch.int32, device=device)
+            crit_m = make_criteria(grna_length=GRNA_LEN, **kw)
+            _lib.screen(genome, q_sub, crit_m, None, c_sub.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            c_sub.zero_()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            _lib.screen(genome, q_sub, crit_m, None, c_sub.data_ptr(), stream=stream)
+            m1.record()
+            torch.cuda.synchronize()
+            sec = m0.elapsed_time(m1) / 1e3
+            other_modes.append({"mode": label, "n_grna": n_sub, "seconds": sec, "value": n_sub * total_bases / 1e9 / sec,
+                                "unit": "gRNA*Gbp/s", "tcell_per_s": 2.0 * n_sub * total_bases / sec / 1e12,
+                                "grna_failed": int(((c_sub[:n_sub] + c_sub[n_sub:]) > 0).sum().item())})
+            if q_sub is not queries:
+                q_sub.free()
+
     # ---- end-to-end through the host-buffer C-ABI call (H2D + pack + tables + screen + D2H)
     e2e = None
     if not args.no_e2e:
@@ -405,7 +432,8 @@ def main():
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bit-sliced 2-bit bases)",
            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * world,
            "roofline": roofline, "cpu_baseline": cpu_baseline, "device": name,
-           "cells_per_s": 2.0 * args.grna * total_bases / (ms_per_step / 1e3), "grna_failed": fails}
+           "cells_per_s": 2.0 * args.grna * total_bases / (ms_per_step / 1e3), "grna_failed": fails,
+           "other_modes": other_modes}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
