@@ -385,6 +385,138 @@ __device__ inline bool verify_nopattern_one_gap(const GenomeView& gv, const Gene
     return false;
 }
 
+// Early reject for the no-pattern criterion with 2..MG_MAX_GAPS gaps (the exhaustive walk below costs ~10^5 operations on
+// a candidate that has no alignment, and most unit-cost edit-distance survivors have none within the gap budget).
+// Lower bound: a trimmed alignment with (mm, g gaps, u unaligned) extends, with the same gaps, to a full-length
+// alignment ending at e with mm' <= mm + u mismatches (off-contig or invalid subject bases count as mismatches), so
+// min over g <= Gp of (fewest mismatches of a full-length alignment with exactly g gaps) + g must be <= M + Gp.
+// f[d][g] = fewest mismatches of query [j, L) against the subject ending at e when query position j sits on diagonal
+// d (subject position e - L + j + d) after g gap characters; the walk goes from j = L down to 0.
+__device__ inline bool nopattern_gaps_infeasible(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
+                                                 int strand, int64_t e, int64_t cs, int64_t ce) {
+    constexpr int GM = MG_MAX_GAPS, W = 2 * GM + 1, INF = 1 << 20;
+    const int L = c.L, Gp = c.Gp, B = c.M + Gp;
+    const int64_t base = e - L;
+    int f[W][GM + 1];
+#pragma unroll
+    for (int d = 0; d < W; ++d)
+#pragma unroll
+        for (int g = 0; g <= GM; ++g) f[d][g] = INF;
+    f[GM][0] = 0;
+    int win[W];                                             // subject bases at base + j - 1 + d, d = -GM..GM (-1: off the contig)
+#pragma unroll
+    for (int d = 0; d < W; ++d) {
+        const int64_t x = base + L - 1 + (d - GM);
+        win[d] = (x >= cs && x < ce) ? tbase(gv, strand, x) : -1;
+    }
+    for (int j = L; j >= 1; --j) {
+        // deletions at query position j (subject base consumed alone): diagonal d -> d - 1, one more gap
+#pragma unroll
+        for (int d = W - 1; d >= 1; --d)
+#pragma unroll
+            for (int g = 0; g < GM; ++g)
+                if (g < Gp) f[d - 1][g + 1] = min(f[d - 1][g + 1], f[d][g]);
+        // query position j - 1: paired with the subject base of its diagonal, or inserted (diagonal d -> d + 1)
+        const int qb = q[j - 1];
+        int nf[W][GM + 1];
+#pragma unroll
+        for (int d = 0; d < W; ++d)
+#pragma unroll
+            for (int g = 0; g <= GM; ++g) {
+                const int mis = (qb >= 4 || qb != win[d]) ? 1 : 0;
+                int v = f[d][g] + mis;
+                if (d >= 1 && g >= 1 && g <= Gp) v = min(v, f[d - 1][g - 1]);
+                nf[d][g] = min(v, INF);
+            }
+#pragma unroll
+        for (int d = 0; d < W; ++d)
+#pragma unroll
+            for (int g = 0; g <= GM; ++g) f[d][g] = nf[d][g];
+        // slide the subject window one base to the left
+#pragma unroll
+        for (int d = W - 1; d >= 1; --d) win[d] = win[d - 1];
+        const int64_t x = base + j - 2 - GM;
+        win[0] = (x >= cs && x < ce) ? tbase(gv, strand, x) : -1;
+    }
+    int best = INF;
+#pragma unroll
+    for (int d = 0; d < W; ++d)
+#pragma unroll
+        for (int g = 0; g <= GM; ++g)
+            if (g <= Gp) best = min(best, f[d][g] + g);
+    return best > B;
+}
+
+// cold call site of the exact no-pattern search below (keeps the unrolled DP small)
+static __device__ __noinline__ bool nopattern_end_ok(const GenomeView& gv, const GeneralCtx& c, int strand, int mm, int gaps,
+                                                     int qs, int qe, int64_t s, int64_t t, int64_t cs, int64_t ce) {
+    const AlnState a{0u, 0u, 0u, 0u, mm, gaps};
+    return alignment_problematic(gv, c, strand, a, qs, qe, s, t, cs, ce);
+}
+
+// Exact verifier for the no-pattern criterion with 2..MG_MAX_GAPS gaps: the criterion (MINORg.py:2018-2044), the position
+// check and the PAM windows only depend on (qs, qe, subject span, #mismatches, #gap characters), so instead of walking
+// every alignment it is enough to know, for each 3' trim qe and each (qs, diagonal, #gaps), the FEWEST mismatches of an
+// E1 alignment (first and last column a base pair, gap characters strictly inside, everything on the contig) - one
+// banded dynamic programme per qe over f[diagonal][gaps], walked from the 3' end like the search it replaces.
+__device__ inline bool verify_nopattern_gaps(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
+                                             int strand, int64_t e, int64_t cs, int64_t ce) {
+    constexpr int GM = MG_MAX_GAPS, W = 2 * GM + 1, INF = 1 << 20;
+    const int L = c.L, M = c.M, Gp = c.Gp, B = M + Gp;
+    const int64_t base = e - L;
+    int sub[MG_MAX_GRNA_LEN + 2 * GM + 2];                  // sub[k] = subject base at base - GM - 1 + k (-1: off the contig)
+    for (int k = 0; k <= L + 2 * GM; ++k) {
+        const int64_t x = base - GM - 1 + k;
+        sub[k] = (x >= cs && x < ce) ? tbase(gv, strand, x) : -1;
+    }
+    for (int qe = L; qe >= 1 && L - qe <= B; --qe) {
+        const int64_t t_end = e - (L - qe);
+        if (t_end - 1 < cs || t_end > ce) continue;          // the last column must be on the contig
+        const int trim3 = L - qe;
+        int f[W][GM + 1];                                    // fewest mismatches of query [j, qe); diagonal d - GM; g gaps
+#pragma unroll
+        for (int d = 0; d < W; ++d)
+#pragma unroll
+            for (int g = 0; g <= GM; ++g) f[d][g] = INF;
+        f[GM][0] = 0;
+        for (int j = qe; j >= 1; --j) {
+            if (j < qe) {
+                // deletion before query position j: consumes subject base + j - 1 + delta; a pair must still fit on the contig
+#pragma unroll
+                for (int d = W - 1; d >= 1; --d) {
+                    const bool room = base + j + (d - GM) - 2 >= cs;
+#pragma unroll
+                    for (int g = 0; g < GM; ++g)
+                        if (g < Gp && room) f[d - 1][g + 1] = min(f[d - 1][g + 1], f[d][g]);
+                }
+            }
+            const int qb = q[j - 1];
+            const int qs = j - 1, u = trim3 + qs;
+            int nf[W][GM + 1];
+#pragma unroll
+            for (int d = 0; d < W; ++d) {
+                const int sb = sub[j + d];                   // subject base + j - 1 + (d - GM)
+                const int mis = (qb >= 4 || qb != sb) ? 1 : 0;
+#pragma unroll
+                for (int g = 0; g <= GM; ++g) {
+                    int v = (sb >= 0 && f[d][g] < INF) ? f[d][g] + mis : INF;     // base pair
+                    if (v > M) v = INF;                      // mismatches only grow
+                    if (v < INF && g <= Gp && (M - v) + (Gp - g) - u >= 0 &&
+                        nopattern_end_ok(gv, c, strand, v, g, qs, qe, base + j - 1 + (d - GM), t_end, cs, ce)) return true;
+                    // insertion of query position j - 1 (not as the last column; a pair must follow)
+                    if (j < qe && j >= 2 && d >= 1 && g >= 1 && g <= Gp) v = min(v, f[d - 1][g - 1]);
+                    nf[d][g] = v;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < W; ++d)
+#pragma unroll
+                for (int g = 0; g <= GM; ++g) f[d][g] = nf[d][g];
+        }
+    }
+    return false;
+}
+
 constexpr int kMaxDepth = MG_MAX_GRNA_LEN + MG_MAX_GAPS + 2;
 
 struct Frame {
@@ -412,6 +544,10 @@ static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const Ge
     const int64_t ce = strand > 0 ? gv.cend[ci] : gv.glen - gv.cstart[ci];
 
     if (c.n_units == 0 && c.Gp <= 1) return verify_nopattern_one_gap(gv, c, q, qpacked, strand, e, cs, ce);
+    if (c.n_units == 0) {
+        if (nopattern_gaps_infeasible(gv, c, q, strand, e, cs, ce)) return false;
+        if (c.Gp <= MG_MAX_GAPS) return verify_nopattern_gaps(gv, c, q, strand, e, cs, ce);
+    }
 
     Frame st[kMaxDepth];
     for (int qe = L; qe >= 1; --qe) {
