@@ -326,7 +326,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
 
     // prefilter over windows [a, b): queues survivors.  strand -1 anchors of a window [p, p+L) end, in
     // reverse-complement coordinates, at glen - p; so windows [a, b) own e' in [glen - b + 1, glen - a + 1).
-    uint32_t* d_tab5 = nullptr;                                   // tables of the bit-sliced edit-distance kernel
+    uint32_t* d_rows_tab = nullptr;                                   // tables of the bit-sliced edit-distance kernel
     const char* gapped_env = getenv("MG_GAPPED_PREFILTER");       // "myers": the one-pattern-per-thread kernel (A/B)
     const bool use_rows = !(gapped_env && strcmp(gapped_env, "myers") == 0);
     // Only the edit-distance rows kernel can also be cut by gRNA group [g0, g1) (groups of 32 gRNA): its threads own
@@ -351,7 +351,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             const int64_t n_anchor = ee - eb;
             if (n_anchor <= 0) continue;
             if (by_myers && use_rows) {
-                const int r2 = launch_gapped_rows(g, q, d_ctx, K, strand, g0, g1, eb, ee, &d_tab5, s);
+                const int r2 = launch_gapped_rows(g, q, d_ctx, K, strand, g0, g1, eb, ee, &d_rows_tab, s);
                 if (r2 != MG_OK) return r2;
             } else if (by_myers) {
                 dim3 grid((unsigned)((n_anchor + kMyersChunk - 1) / kMyersChunk), (unsigned)((q->n + kMyersThreads - 1) / kMyersThreads), 1);
@@ -440,7 +440,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     if (trace) fprintf(stderr, "[mg_screen general] prefilter=%s K=%d survivors=%llu slices=%d prefilter %.1f ms verify %.1f ms\n",
                        by_pieces ? "pieces" : by_hamming ? "hamming" : by_myers ? (use_rows ? "edit-rows" : "myers") : "all-cells", K, total_cand, n_slices,
                        t_prefilter * 1e3, t_verify * 1e3);
-    dev_free(d_tab5, s);
+    dev_free(d_rows_tab, s);
     dev_free(h.cand, s);
     dev_free(h.cand_count, s);
     cudaFree(d_ctx);
