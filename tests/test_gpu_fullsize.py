@@ -106,6 +106,50 @@ def test_window_shards_add_up_and_strand_symmetry(world):
     assert np.array_equal(_screen(world, [_rc(g) for g in world["grnas"]], M), whole)
 
 
+def _screen_crit(w, grnas, kw, win=(0, -1), masks=None):
+    from minorg_b200.ot_regex import make_criteria
+    torch, L_ = w["torch"], w["lib"]
+    w["genome"].set_masks(masks or [])
+    q = L_.Queries(grnas, stream=w["stream"])
+    counts = torch.zeros(2 * len(grnas), dtype=torch.int32, device="cuda")
+    L_.screen(w["genome"], q, make_criteria(grna_length=L, **kw), None, counts.data_ptr(), win_begin=win[0], win_end=win[1],
+              stream=w["stream"])
+    c = counts.cpu().numpy().astype(np.int64)
+    q.free()
+    return c
+
+
+def test_gapped_screen_full_size_properties(world):
+    """Gapped criterion (<=1 mismatch / <=1 gap: edit-distance rows kernel + closed-form verifier) over the whole 135 Mb:
+    * monotone: every gRNA counts at least its ungapped <=1-mismatch hits (those alignments are in the gapped universe);
+    * a gRNA with one base deleted or inserted in the middle finds the exact plant of the original gRNA through one gap;
+      searched WITHOUT gaps (ot_gap=1) it does not;
+    * window shards add up; a gRNA and its reverse complement swap their '+' and '-' verdicts."""
+    grnas = world["grnas"]
+    n = len(grnas)
+    ung = _screen(world, grnas, 1)
+    gap = _screen_crit(world, grnas, dict(ot_mismatch=2, ot_gap=2))
+    assert ((gap[:n] + gap[n:]) >= ung).all()
+    # edited copies of the first 48 gRNA (each has an exact plant): drop base 9 and append a base / insert a base at 9
+    rng = np.random.Generator(np.random.PCG64(11))
+    dele = [g[:9] + g[10:] + "ACGT"[int(rng.integers(0, 4))] for g in grnas[:48]]
+    ins = [g[:9] + "ACGT"[int(rng.integers(0, 4))] + g[9:19] for g in grnas[:48]]
+    # deleted base: 19 positions align with one gap, the appended base is a mismatch or trimmed => needs M = 1, Gp = 1;
+    # inserted base: all 20 positions are consumed (19 pairs + the insertion) => M = 0, Gp = 1 is enough
+    for edited, mm in ((dele, 2), (ins, 1)):
+        with_gap = _screen_crit(world, edited, dict(ot_mismatch=mm, ot_gap=2))
+        assert ((with_gap[:48] + with_gap[48:]) >= 1).all()
+        no_gap = _screen_crit(world, edited, dict(ot_mismatch=mm, ot_gap=1))
+        assert (no_gap[:48] + no_gap[48:]).sum() <= 6          # chance only (expected 0.7 at <=1 mismatch)
+    glen = world["genome"].global_length
+    cuts = [0, glen // 8 + 5, glen // 2, glen // 2 + 1, glen]
+    parts = sum(_screen_crit(world, grnas, dict(ot_mismatch=2, ot_gap=2), win=(a, b)) for a, b in zip(cuts[:-1], cuts[1:]))
+    assert np.array_equal(gap, parts)
+    rc = _screen_crit(world, [_rc(g) for g in grnas], dict(ot_mismatch=2, ot_gap=2))
+    # counts are distinct virtual 3' ends, which a reversed alignment set need not preserve; the verdicts are symmetric
+    assert np.array_equal(rc[:n] > 0, gap[n:] > 0) and np.array_equal(rc[n:] > 0, gap[:n] > 0)
+
+
 def test_human_scale_genome_beyond_2_31(tmp_path):
     """BASELINE configs[4] shape: one 3.1 Gbp genome (24 contigs).  Global coordinates exceed 2^31, so every position
     computation on the path must be 64-bit: hits planted near the END of the genome are found, in every window
