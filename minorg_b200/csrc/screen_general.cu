@@ -304,6 +304,13 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     MG_CUDA(dev_alloc((void**)&h.cand, sizeof(Cand) * h.cand_cap, s));
     MG_CUDA(dev_alloc((void**)&h.cand_count, 8, s));
     MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
+    int K = crit->n_units ? crit->prefilter_edits : crit->max_mismatch + crit->max_gap;
+    if (K >= L) K = -1;
+    const char* pf_env = getenv("MG_PREFILTER");        // "none": hand EVERY anchor to the verifier (tests: prefilter soundness)
+    const bool no_prefilter = pf_env && strcmp(pf_env, "none") == 0;
+    // gapped patterns: the verifier drops a candidate whose cheapest full-length alignment within the gap cap already
+    // exceeds the host-proved bound, before the exhaustive walk (not in the soundness-test mode, which must not rely on it)
+    h.edit_bound = (crit->n_units > 0 && crit->max_gap >= 1 && K >= 0 && !no_prefilter) ? K : -1;
     GeneralCtx* d_ctx = nullptr;
     MG_CUDA(cudaMalloc(&d_ctx, sizeof h));
     int rc = MG_OK;
@@ -312,10 +319,6 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     if (e != cudaSuccess) { cudaFree(d_ctx); dev_free(h.cand, s); dev_free(h.cand_count, s); set_error("copying criteria: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
 
     // anchors (virtual ends, exclusive) owned by the window range [wb, we): e = p + L
-    int K = crit->n_units ? crit->prefilter_edits : crit->max_mismatch + crit->max_gap;
-    if (K >= L) K = -1;
-    const char* pf_env = getenv("MG_PREFILTER");        // "none": hand EVERY anchor to the verifier (tests: prefilter soundness)
-    const bool no_prefilter = pf_env && strcmp(pf_env, "none") == 0;
     const bool by_pieces = !no_prefilter && h.n_pieces > 0;
     const bool by_hamming = !no_prefilter && !by_pieces && crit->max_gap == 0 && K >= 0;
     const bool by_myers = !no_prefilter && !by_pieces && !by_hamming && K >= 0;

@@ -32,6 +32,7 @@ struct GeneralCtx {
     PamSideDev five, three;
     int32_t five_max, three_max;
     int32_t prune_pattern;    // 1: partial pattern evaluation is a sound lower bound (Gp <= 1: no 'dd' elements)
+    int32_t edit_bound;       // >= 0: host-proved bound of a gapped pattern (true => mm + gaps + unaligned <= this); -1: none
     int32_t n_pieces;         // exact-piece prefilter: position masks in gRNA orientation and mirrored (rc queries)
     uint32_t piece_fwd[MG_MAX_PIECES], piece_rev[MG_MAX_PIECES];
     // prefilter survivors are queued here and verified by a second kernel with one thread per candidate
@@ -389,13 +390,14 @@ __device__ inline bool verify_nopattern_one_gap(const GenomeView& gv, const Gene
 // a candidate that has no alignment, and most unit-cost edit-distance survivors have none within the gap budget).
 // Lower bound: a trimmed alignment with (mm, g gaps, u unaligned) extends, with the same gaps, to a full-length
 // alignment ending at e with mm' <= mm + u mismatches (off-contig or invalid subject bases count as mismatches), so
-// min over g <= Gp of (fewest mismatches of a full-length alignment with exactly g gaps) + g must be <= M + Gp.
+// min over g <= Gp of (fewest mismatches of a full-length alignment with exactly g gaps) + g must be <= B, where B is
+// M + Gp for the no-pattern criterion or the host-proved edit bound of a pattern (ot_regex.edit_bound).
 // f[d][g] = fewest mismatches of query [j, L) against the subject ending at e when query position j sits on diagonal
 // d (subject position e - L + j + d) after g gap characters; the walk goes from j = L down to 0.
-__device__ inline bool nopattern_gaps_infeasible(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
-                                                 int strand, int64_t e, int64_t cs, int64_t ce) {
+__device__ inline bool gapped_cost_exceeds(const GenomeView& gv, const GeneralCtx& c, const uint8_t* __restrict__ q,
+                                           int strand, int64_t e, int64_t cs, int64_t ce, int B) {
     constexpr int GM = MG_MAX_GAPS, W = 2 * GM + 1, INF = 1 << 20;
-    const int L = c.L, Gp = c.Gp, B = c.M + Gp;
+    const int L = c.L, Gp = c.Gp;
     const int64_t base = e - L;
     int f[W][GM + 1];
 #pragma unroll
@@ -545,9 +547,11 @@ static __device__ __noinline__ bool verify_anchor(const GenomeView& gv, const Ge
 
     if (c.n_units == 0 && c.Gp <= 1) return verify_nopattern_one_gap(gv, c, q, qpacked, strand, e, cs, ce);
     if (c.n_units == 0) {
-        if (nopattern_gaps_infeasible(gv, c, q, strand, e, cs, ce)) return false;
+        if (gapped_cost_exceeds(gv, c, q, strand, e, cs, ce, c.M + c.Gp)) return false;
         if (c.Gp <= MG_MAX_GAPS) return verify_nopattern_gaps(gv, c, q, strand, e, cs, ce);
     }
+
+    if (c.edit_bound >= 0 && gapped_cost_exceeds(gv, c, q, strand, e, cs, ce, c.edit_bound)) return false;
 
     Frame st[kMaxDepth];
     for (int qe = L; qe >= 1; --qe) {
