@@ -34,7 +34,7 @@ def main():
         ("pattern 0mg-10,1mg-11- with <=1 gap (config 3)", 135e6, 10000, 20, dict(ot_pattern="0mg-10,1mg-11-", ot_gap=2), ".NGG"),
         ("two gaps: <=2 mm / <=2 gaps (edit distance K=4, banded-DP verifier)", 135e6, 2048, 20, dict(ot_mismatch=3, ot_gap=3), ".NGG"),
         ("two gaps: <=4 mm / <=2 gaps (edit distance K=6, banded-DP verifier)", 135e6, 1024, 20, dict(ot_mismatch=5, ot_gap=3), ".NGG"),
-        ("pattern 5mg1- with <=1 gap (edit distance K=5, DFS verifier with pattern pruning)", 135e6, 1024, 20, dict(ot_pattern="5mg1-", ot_gap=2), ".NGG"),
+        ("pattern 5mg1- with <=1 gap (edit distance K=5; bound reject + DFS verifier)", 135e6, 1024, 20, dict(ot_pattern="5mg1-", ot_gap=2), ".NGG"),
         ("Cas12a 23-nt gapped <=4 mm / <=1 gap + PAM proximity TTTV.", 135e6, 2048, 23, dict(ot_mismatch=5, ot_gap=2, ot_pamless=False), "TTTV."),
     ]
     only = sys.argv[1:]
