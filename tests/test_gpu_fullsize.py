@@ -206,4 +206,23 @@ def test_human_scale_genome_beyond_2_31(tmp_path):
     masked = run()
     assert np.array_equal(whole[:32] - masked[:32], np.ones(32, dtype=np.int64)) and np.array_equal(whole[32:], masked[32:])
     q.free()
+    # the gapped path (edit-distance rows kernel, survivor queue, verifier) with 64-bit coordinates: gRNA with one base
+    # inserted find their plants beyond 2^31 through one gap, the masks (still set) remove exactly the masked ones, and
+    # the 8 window shards add up
+    edited = [g[:9] + "C" + g[9:19] for g in grnas[:64]]
+    qg = _lib.Queries(edited, stream=stream)
+    critg = make_criteria(ot_mismatch=1, ot_gap=2, grna_length=L)
+
+    def run_gapped(win=(0, -1)):
+        counts = torch.zeros(2 * 64, dtype=torch.int32, device="cuda")
+        _lib.screen(genome, qg, critg, None, counts.data_ptr(), win_begin=win[0], win_end=win[1], stream=stream)
+        c = counts.cpu().numpy().astype(np.int64)
+        return c[:64] + c[64:]
+    gm = run_gapped()
+    genome.set_masks([])
+    gw = run_gapped()
+    assert (gw >= 1).all()
+    assert ((gw[:32] - gm[:32]) >= 1).all() and np.array_equal(gw[32:], gm[32:])
+    assert np.array_equal(sum(run_gapped(shard_windows(genome.global_length, L, r, 8)) for r in range(8)), gw)
+    qg.free()
     genome.free()
