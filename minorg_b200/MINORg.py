@@ -102,6 +102,11 @@ class MINORg:
         self.exclude = None
         self.masked = {}
         self._genomes = {}
+        # Not a reference attribute.  False (default): every cell of every subject is evaluated and the per-gRNA COUNTS are
+        # exact (what bench.py and the parity tests measure).  True: filter_background only needs pass/fail, so each
+        # subject is screened in window slices and a gRNA that already has an off-target leaves the query set - same
+        # verdicts, the counts are lower bounds.  Most useful for the gapped criteria, where most gRNA fail early.
+        self.screen_verdicts_only = False
         dev = int(os.environ.get("MINORG_B200_DEVICE", "0")) if device is None else int(device)
         self.device_name, self.device_sms = _lib.init(dev)
         for k, v in kwargs.items():
@@ -297,15 +302,30 @@ class MINORg:
             by_len.setdefault(len(s), []).append(i)
         stream = torch.cuda.current_stream().cuda_stream
         for length, idx in by_len.items():
-            q = _lib.Queries([seqs[i] for i in idx], stream=stream)
-            counts = torch.zeros(2 * len(idx), dtype=torch.int32, device="cuda")
             pam = PAM(self.pam, length).program() if not self.ot_pamless else None
             wb, we = (0, -1) if windows is None else _dist.shard_windows(genome.global_length, length, *windows)
-            if windows is None or we > wb:
-                _lib.screen(genome, q, self._criteria(length), pam, counts.data_ptr(), win_begin=wb, win_end=we, stream=stream)
-            c = counts.cpu().numpy().astype(np.int64)
-            out[idx] = c[:len(idx)] + c[len(idx):]
-            q.free()
+            if windows is not None and we <= wb:
+                continue
+            if we < 0:
+                we = max(0, genome.global_length - length + 1)
+            crit = self._criteria(length)
+            # exact counts: one pass.  verdicts only: geometric window slices, survivors only carry on
+            n_slices = 12 if self.screen_verdicts_only else 1
+            cuts = [wb + ((we - wb) >> (n_slices - 1 - k)) // 32 * 32 for k in range(n_slices - 1)] + [we]
+            alive, begin = list(idx), wb
+            for end in cuts:
+                if end <= begin or not alive:
+                    continue
+                q = _lib.Queries([seqs[i] for i in alive], stream=stream)
+                counts = torch.zeros(2 * len(alive), dtype=torch.int32, device="cuda")
+                _lib.screen(genome, q, crit, pam, counts.data_ptr(), win_begin=begin, win_end=end, stream=stream)
+                c = counts.cpu().numpy().astype(np.int64)
+                c = c[:len(alive)] + c[len(alive):]
+                out[alive] += c
+                q.free()
+                if self.screen_verdicts_only:
+                    alive = [i for i, x in zip(alive, c) if x == 0]
+                begin = end
         return out
 
     def _offtarget_hits(self, fasta_subject, keep_output=False, fout=None, thread=None):

@@ -123,6 +123,28 @@ def test_config1_pattern_and_pam_modes(cfg1, tmp_path):
         m.close()
 
 
+def test_verdicts_only_mode_gives_the_same_verdicts(cfg1, tmp_path):
+    """screen_verdicts_only (not a reference attribute; off by default): window slices with the failed gRNA dropped from
+    the query set give the same pass/fail as the exhaustive counting screen, for the ungapped and the gapped criterion."""
+    from minorg_b200.MINORg import MINORg
+    for kw in (dict(ot_mismatch=2), dict(ot_mismatch=2, ot_gap=2)):
+        verdicts = []
+        for fast in (False, True):
+            m = MINORg(directory=str(tmp_path / ("v%d%d" % (fast, len(kw)))), prefix="v")
+            for k, v in kw.items():
+                setattr(m, k, v)
+            m.screen_verdicts_only = fast
+            m.target = str(cfg1 / "targets.fasta")
+            m.reference = {"TAIR10": str(cfg1 / "subset_ref_TAIR10.fasta")}
+            m.add_query(str(cfg1 / "subset_9654.fasta"), alias="9654")
+            m.grna()
+            m.filter_background()
+            verdicts.append([m.grna_hits.get_gRNAseq_by_seq(s).check("background") for s in m.grna_hits.seqs])
+            m.close()
+        assert verdicts[0] == verdicts[1], kw
+        assert True in verdicts[0] and False in verdicts[0], kw
+
+
 def test_cli_full_then_resume_from_map(cfg1, tmp_path):
     """`python -m minorg_b200 full ...` and a second `filter` + `minimumset` run resumed from the .map file."""
     from minorg_b200.__main__ import main
