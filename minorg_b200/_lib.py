@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libminorg_b200.so")
+LIB_PATH = os.environ.get("MINORG_B200_LIB") or os.path.join(_HERE, "libminorg_b200.so")   # override: A/B builds
 
 MG_MAX_GRNA_LEN = 32
 MG_MAX_PAM_LEN = 16
