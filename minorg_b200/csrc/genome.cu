@@ -129,8 +129,10 @@ static int genome_alloc(const int64_t* offsets, int n_contigs, cudaStream_t s, m
     MG_CUDA(cudaMalloc(&g->d_cstart, nb));
     MG_CUDA(cudaMalloc(&g->d_cend, nb));
     if (n_contigs) {
-        MG_CUDA(cudaMemcpy(g->d_cstart, g->cstart.data(), sizeof(int64_t) * n_contigs, cudaMemcpyHostToDevice));
-        MG_CUDA(cudaMemcpy(g->d_cend, g->cend.data(), sizeof(int64_t) * n_contigs, cudaMemcpyHostToDevice));
+        // on the caller's stream (a plain cudaMemcpy would join the legacy default stream and wait for a screen running there);
+        // the host vectors live in the handle and every creator synchronises the stream before returning
+        MG_CUDA(cudaMemcpyAsync(g->d_cstart, g->cstart.data(), sizeof(int64_t) * n_contigs, cudaMemcpyHostToDevice, s));
+        MG_CUDA(cudaMemcpyAsync(g->d_cend, g->cend.data(), sizeof(int64_t) * n_contigs, cudaMemcpyHostToDevice, s));
     }
     guard.armed = false;
     *out = g;
