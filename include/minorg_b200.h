@@ -167,7 +167,9 @@ int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, 
 
 /* Host-buffer convenience around the calls above (the end-to-end path timed by bench.py "e2e"):
  * ASCII genome + ASCII gRNAs in host memory -> H2D, pack, screen, D2H.  counts_out: N uint32 (both
- * orientations summed). */
+ * orientations summed).  The subject is processed in batches of whole contigs; the next batch is copied and
+ * packed on an internal stream while the current one is screened on `stream` (pinned `seq` makes that copy
+ * asynchronous).  Returns after everything, including the D2H of the counts, has completed. */
 int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
                    const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
                    const char* grna, int n, int len, const mg_criteria* crit, const mg_pam* pam,
