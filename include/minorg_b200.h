@@ -52,8 +52,23 @@ int mg_init(int device, char* name_out, int name_cap, int* sm_count_out);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct mg_genome mg_genome;
 
+/* Native FASTA reader (host threads; plain files): what the reference does with Bio.SeqIO / pyfaidx before it can
+ * hand a subject to blastn (fasta.py:21-43, index.py:150-211).  A header line starts with '>'; the record id is the
+ * first whitespace-delimited token of the header; the sequence is every byte up to the next header line except
+ * '\n', '\r', ' ' and '\t' (case preserved); bytes before the first header are ignored.  threads <= 0: all cores. */
+typedef struct mg_fasta mg_fasta;
+int mg_fasta_read(const char* path, int threads, mg_fasta** out);
+int mg_fasta_n_records(const mg_fasta* f);
+const char* mg_fasta_name(const mg_fasta* f, int i);
+const int64_t* mg_fasta_offsets(const mg_fasta* f);      /* n_records + 1 */
+const char* mg_fasta_sequence(const mg_fasta* f);        /* offsets[n_records] bytes, records concatenated */
+void mg_fasta_free(mg_fasta* f);
+
 /* seq: concatenated ASCII contig sequences (host); contig i = seq[offsets[i], offsets[i+1]).  */
 int mg_genome_from_ascii(const char* seq, const int64_t* offsets, int n_contigs, void* stream, mg_genome** out);
+/* mg_fasta_read + mg_genome_from_ascii.  fasta_out (may be NULL) receives the parsed file (names, offsets, host
+ * sequence) - the caller frees it with mg_fasta_free. */
+int mg_genome_from_fasta(const char* path, int threads, void* stream, mg_genome** out, mg_fasta** fasta_out);
 /* Same, with the ASCII bytes already on the device (synthetic-genome benchmarks). */
 int mg_genome_from_device_ascii(const char* d_seq, const int64_t* offsets, int n_contigs, void* stream,
                                 mg_genome** out);

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import _lib
-from .fasta import fasta_to_dict, read_fasta, read_fasta_arrays, reverse_complement
+from .fasta import fasta_to_dict, read_fasta, reverse_complement
 from . import distributed as _dist
 from .generate_grna import find_multi_gRNA
 from .minimum_set import minimum_sets
@@ -225,8 +225,8 @@ class MINORg:
         """Packed genome of a FASTA file, resident in HBM (cached per file): (handle, contig names)."""
         fname = _fname(fname)
         if fname not in self._genomes:
-            blob, offsets, names = read_fasta_arrays(fname)
-            self._genomes[fname] = (_lib.Genome.from_host_array(blob, offsets, names), names)
+            genome = _lib.Genome.from_fasta(fname)      # native reader (host threads) + H2D + 2-bit pack
+            self._genomes[fname] = (genome, genome.names)
         return self._genomes[fname]
 
     @staticmethod

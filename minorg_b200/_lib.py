@@ -27,6 +27,8 @@ EXPORTS = [
     "mg_mask_find", "mg_enumerate_sites", "mg_queries_create", "mg_queries_count", "mg_queries_length",
     "mg_queries_free", "mg_screen", "mg_screen_host", "mg_genome_contig_global_start", "mg_genome_global_length",
     "mg_microbench", "mg_last_screen_stats",
+    "mg_fasta_read", "mg_fasta_n_records", "mg_fasta_name", "mg_fasta_offsets", "mg_fasta_sequence", "mg_fasta_free",
+    "mg_genome_from_fasta",
 ]
 
 
@@ -101,6 +103,17 @@ def lib():
                                  C.POINTER(Pam), vp, vp]
     L.mg_microbench.argtypes = [C.c_int, C.POINTER(C.c_double), vp]
     L.mg_last_screen_stats.argtypes = [C.POINTER(C.c_uint64)]
+    L.mg_fasta_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.mg_fasta_n_records.argtypes = [vp]
+    L.mg_fasta_name.argtypes = [vp, C.c_int]
+    L.mg_fasta_name.restype = C.c_char_p
+    L.mg_fasta_offsets.argtypes = [vp]
+    L.mg_fasta_offsets.restype = i64p
+    L.mg_fasta_sequence.argtypes = [vp]
+    L.mg_fasta_sequence.restype = vp
+    L.mg_fasta_free.argtypes = [vp]
+    L.mg_fasta_free.restype = None
+    L.mg_genome_from_fasta.argtypes = [C.c_char_p, C.c_int, vp, C.POINTER(vp), C.POINTER(vp)]
     _lib = L
     return L
 
@@ -117,6 +130,26 @@ def _ptr(a):
 
 def _i64(a):
     return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def read_fasta_native(path, threads=0):
+    """Native FASTA reader (mg_fasta_read; host threads, no GPU involved) -> (uint8 array of the concatenated sequence
+    bytes, int64 offsets[n+1], names): same result as minorg_b200.fasta.read_fasta_arrays."""
+    f = C.c_void_p()
+    check(lib().mg_fasta_read(os.fsencode(path), int(threads), C.byref(f)), "mg_fasta_read")
+    try:
+        n = lib().mg_fasta_n_records(f)
+        offsets = np.ctypeslib.as_array(lib().mg_fasta_offsets(f), shape=(n + 1,)).copy()
+        names = [lib().mg_fasta_name(f, i).decode("latin-1") for i in range(n)]
+        total = int(offsets[-1])
+        if total:
+            buf = (C.c_uint8 * total).from_address(lib().mg_fasta_sequence(f))
+            blob = np.frombuffer(buf, dtype=np.uint8).copy()
+        else:
+            blob = np.zeros(1, dtype=np.uint8)
+    finally:
+        lib().mg_fasta_free(f)
+    return blob, offsets, names
 
 
 def init(device=0):
@@ -158,6 +191,18 @@ class Genome:
         h = C.c_void_p()
         check(lib().mg_genome_from_ascii(_ptr(arr), _i64(offsets), len(offsets) - 1, C.c_void_p(stream), C.byref(h)),
               "mg_genome_from_ascii")
+        return cls(h.value, names)
+
+    @classmethod
+    def from_fasta(cls, path, threads=0, stream=0):
+        """Plain FASTA file -> resident genome through the native reader (mg_genome_from_fasta); names from the file."""
+        h, f = C.c_void_p(), C.c_void_p()
+        check(lib().mg_genome_from_fasta(os.fsencode(path), int(threads), C.c_void_p(stream), C.byref(h), C.byref(f)),
+              "mg_genome_from_fasta")
+        try:
+            names = [lib().mg_fasta_name(f, i).decode("latin-1") for i in range(lib().mg_fasta_n_records(f))]
+        finally:
+            lib().mg_fasta_free(f)
         return cls(h.value, names)
 
     @classmethod

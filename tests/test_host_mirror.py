@@ -358,3 +358,49 @@ def test_edit_distance_rows_arithmetic_identities():
                 d = new[k, i] - (new[k, i - 1] if i else 0)
                 assert ((Pv[i] >> k) & 1, (Mv[i] >> k) & 1) == (int(d == 1), int(d == -1))
         col = new
+
+
+def test_native_fasta_reader_matches_python_reader(tmp_path):
+    """mg_fasta_read (host threads inside libminorg_b200.so; no GPU involved) against the numpy reader, which follows the
+    record semantics of the reference's FASTA handling: ids, offsets and sequence bytes, on awkward files."""
+    import os
+    import random
+    import numpy as np
+    from minorg_b200 import _lib
+    from minorg_b200.fasta import read_fasta_arrays
+    here = os.path.dirname(__file__)
+    rng = random.Random(9)
+    body = "".join(rng.choice("ACGTacgtNn") for _ in range(5000))
+    big = "".join(rng.choice("ACGT") for _ in range(9_500_000))           # several 4 MB work items, one record
+    cases = {
+        "plain": ">a desc\nACGT\nAC\n>b\nTTTT\n",
+        "no_final_newline": ">a\nACGT\n>b\nGG",
+        "crlf": ">a x\r\nACGT\r\nAC\r\n>b\r\nT T\tT\r\n",
+        "junk_before_first_header": "garbage\nlines\n>a\nAC\n",
+        "empty_records": ">a\n>b\n\n\n>c\nA\n>d",
+        "header_only": ">only",
+        "no_header": "ACGT\nACGT\n",
+        "empty": "",
+        "gt_inside_line": ">a\nAC>GT\nA\n>b\n>",
+        "blank_and_spaces": ">a\n\n  AC GT \n\t\nNN\n",
+        "header_tabs": ">\tid1\tdescription here\nACGT\n> id2 \nGG\n",
+        "long_lines": ">x\n" + body + "\n>y\n" + "\n".join(body[i:i + 61] for i in range(0, len(body), 61)) + "\n",
+        "big": ">chrBig\n" + "\n".join(big[i:i + 80] for i in range(0, len(big), 80)) + "\n>tail\nACGT\n",
+    }
+    for name, text in cases.items():
+        p = tmp_path / (name + ".fa")
+        p.write_bytes(text.encode("latin-1"))
+        want = read_fasta_arrays(str(p))
+        for threads in (1, 3, 0):
+            got = _lib.read_fasta_native(str(p), threads)
+            assert got[2] == want[2], (name, got[2], want[2])
+            assert np.array_equal(got[1], want[1]), (name, got[1], want[1])
+            n = int(want[1][-1])
+            assert np.array_equal(got[0][:n], want[0][:n]), name
+    for fixture in ("sample_CDS.fasta", "synth_targets.fasta", "synth_cover.fasta"):
+        path = os.path.join(here, "golden", fixture)
+        if os.path.exists(path):
+            want, got = read_fasta_arrays(path), _lib.read_fasta_native(path)
+            assert got[2] == want[2] and np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), fixture
+    with pytest.raises(_lib.MinorgB200Error):
+        _lib.read_fasta_native(str(tmp_path / "does_not_exist.fa"))
