@@ -542,3 +542,53 @@ def gen_eqv():
 
 if __name__ == "__main__" and "eqv" in sys.argv[1:]:
     gen_eqv()
+
+
+# ----------------------------------------------------------------------------- .map reader
+def gen_mapfile():
+    """gRNAHits.parse_from_mapping (grna.py:447-514) on the reference's own fixture examples/sample_custom_check.map
+    (format version 2: 'group' column, no target length, a user check column) and on the same rows rewritten in the
+    other header versions (1: '[start, end)' range; 3/5: with target length; 4: 'set' without length).  Dumped: what the
+    reader restored, and the version-5 text the reference's writer produces from it."""
+    import tempfile
+    from minorg.grna import gRNAHits
+    src = open("/root/reference/examples/sample_custom_check.map").read().splitlines()
+    header, data = src[0].split("\t"), [ln.split("\t") for ln in src[1:] if ln.strip()]
+    gi = header.index("group")
+    variants = {"v2_fixture": "\n".join(src) + "\n"}
+    h1 = header[:5] + ["range (0-index, end exclusive)"] + header[7:]
+    variants["v1"] = "\n".join(["\t".join(h1)] + ["\t".join(r[:5] + ["[%d, %d)" % (int(r[5]) - 1, int(r[6]))] + r[7:]) for r in data]) + "\n"
+    h3 = header[:3] + ["target length"] + header[3:]
+    variants["v3"] = "\n".join(["\t".join(h3)] + ["\t".join(r[:3] + ["500"] + r[3:]) for r in data]) + "\n"
+    h4 = [("set" if x == "group" else x) for x in header]
+    variants["v4"] = "\n".join(["\t".join(h4)] + ["\t".join(r) for r in data]) + "\n"
+    h5 = [("set" if x == "group" else x) for x in h3]
+    variants["v5"] = "\n".join(["\t".join(h5)] + ["\t".join(r[:3] + ["500"] + r[3:]) for r in data]) + "\n"
+    assert gi == 7
+    rows = []
+    with tempfile.TemporaryDirectory() as td:
+        for name, text in variants.items():
+            p = os.path.join(td, name + ".map")
+            with open(p, "w") as f:
+                f.write(text)
+            h = gRNAHits()
+            try:
+                quiet(h.parse_from_mapping, p)
+            except Exception as e:             # version 1 hits `re` without an import in grna.py:478 -> NameError
+                rows.append(dict(name=name, map_text=text, error=type(e).__name__))
+                continue
+            restored = []
+            for seq in h.seqs:
+                gs = h.get_gRNAseq_by_seq(seq)
+                hits = sorted(h.get_hits(seq), key=lambda x: (x.target_id, x.range[0]))
+                restored.append([seq, gs.id, {k: gs.check(k) for k in sorted(gs._checks)},
+                                 [[x.target_id, x.range[0], x.range[1], x.strand, x.hit_id, x.target_len, x.parent_sense(),
+                                   {k: x.check(k) for k in sorted(x._checks)}] for x in hits]])
+            out = os.path.join(td, name + ".out.map")
+            quiet(h.write_mapping, out, write_all=True, write_checks=True)
+            rows.append(dict(name=name, map_text=text, restored=restored, rewritten=open(out).read()))
+    dump("mapfile.json", dict(rows=rows))
+
+
+if __name__ == "__main__" and "mapfile" in sys.argv[1:]:
+    gen_mapfile()
