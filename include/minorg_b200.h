@@ -180,6 +180,11 @@ typedef struct {
 int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
               int64_t win_begin, int64_t win_end, uint32_t* d_counts, void* stream);
 
+/* mg_screen on resident handles with the 2*N counts returned in HOST memory (device scratch inside the library):
+ * what the Python mirror of MINORg._offtarget_hits calls, so that a single-GPU run needs no device-array package. */
+int mg_screen_to_host(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
+                      int64_t win_begin, int64_t win_end, uint32_t* counts_out, void* stream);
+
 /* Host-buffer convenience around the calls above (the end-to-end path timed by bench.py "e2e"):
  * ASCII genome + ASCII gRNAs in host memory -> H2D, pack, screen, D2H.  counts_out: N uint32 (both
  * orientations summed).  The subject is processed in batches of whole contigs; the next batch is copied and

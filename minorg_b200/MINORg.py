@@ -232,6 +232,9 @@ class MINORg:
     @staticmethod
     def _ranks():
         """(rank, world) of the torch.distributed job this process belongs to, (0, 1) outside one."""
+        import sys
+        if "torch" not in sys.modules:          # a process group can only exist if torch is already loaded;
+            return 0, 1                         # a single-GPU run never pays for importing it
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
@@ -291,7 +294,6 @@ class MINORg:
         """Per-sequence count of problematic, unmasked alignments in one subject file (device screen).
         windows=(rank, world) restricts the scan to that rank's share of the window starts (one genome split
         over several GPUs; the caller sums the shares, e.g. with distributed.allreduce_counts)."""
-        import torch
         fname = _fname(fasta_subject)
         genome, names = self._genome(fname)
         index = {n: i for i, n in enumerate(names)}
@@ -300,7 +302,7 @@ class MINORg:
         by_len = {}
         for i, s in enumerate(seqs):
             by_len.setdefault(len(s), []).append(i)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = 0
         for length, idx in by_len.items():
             pam = PAM(self.pam, length).program() if not self.ot_pamless else None
             wb, we = (0, -1) if windows is None else _dist.shard_windows(genome.global_length, length, *windows)
@@ -317,9 +319,7 @@ class MINORg:
                 if end <= begin or not alive:
                     continue
                 q = _lib.Queries([seqs[i] for i in alive], stream=stream)
-                counts = torch.zeros(2 * len(alive), dtype=torch.int32, device="cuda")
-                _lib.screen(genome, q, crit, pam, counts.data_ptr(), win_begin=begin, win_end=end, stream=stream)
-                c = counts.cpu().numpy().astype(np.int64)
+                c = _lib.screen_counts(genome, q, crit, pam, win_begin=begin, win_end=end, stream=stream).astype(np.int64)
                 c = c[:len(alive)] + c[len(alive):]
                 out[alive] += c
                 q.free()

@@ -28,7 +28,7 @@ EXPORTS = [
     "mg_queries_free", "mg_screen", "mg_screen_host", "mg_genome_contig_global_start", "mg_genome_global_length",
     "mg_microbench", "mg_last_screen_stats",
     "mg_fasta_read", "mg_fasta_n_records", "mg_fasta_name", "mg_fasta_offsets", "mg_fasta_sequence", "mg_fasta_free",
-    "mg_genome_from_fasta",
+    "mg_genome_from_fasta", "mg_screen_to_host",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
     L.mg_queries_free.argtypes = [vp]
     L.mg_queries_free.restype = None
     L.mg_screen.argtypes = [vp, vp, C.POINTER(Criteria), C.POINTER(Pam), C.c_int64, C.c_int64, vp, vp]
+    L.mg_screen_to_host.argtypes = [vp, vp, C.POINTER(Criteria), C.POINTER(Pam), C.c_int64, C.c_int64, vp, vp]
     L.mg_screen_host.argtypes = [vp, i64p, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(Criteria),
                                  C.POINTER(Pam), vp, vp]
     L.mg_microbench.argtypes = [C.c_int, C.POINTER(C.c_double), vp]
@@ -325,6 +326,14 @@ def screen(genome, queries, criteria, pam, d_counts_ptr, win_begin=0, win_end=-1
     """Adds per-query problematic-alignment counts into the DEVICE array d_counts_ptr (2N uint32)."""
     check(lib().mg_screen(genome.handle, queries.handle, C.byref(criteria), C.byref(pam) if pam is not None else None,
                           int(win_begin), int(win_end), C.c_void_p(d_counts_ptr), C.c_void_p(stream)), "mg_screen")
+
+
+def screen_counts(genome, queries, criteria, pam, win_begin=0, win_end=-1, stream=0):
+    """mg_screen_to_host: per-query counts of one screen as a host uint32[2N] array (no device-array package needed)."""
+    out = np.zeros(max(1, 2 * queries.n), dtype=np.uint32)
+    check(lib().mg_screen_to_host(genome.handle, queries.handle, C.byref(criteria), C.byref(pam) if pam is not None else None,
+                                  int(win_begin), int(win_end), _ptr(out), C.c_void_p(stream)), "mg_screen_to_host")
+    return out[:2 * queries.n]
 
 
 def screen_host(arr, offsets, masks, grna_blob, n, length, criteria, pam, stream=0):

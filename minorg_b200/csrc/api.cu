@@ -186,6 +186,28 @@ int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, 
     return launch_screen_general(g, q, crit, pam, win_begin, win_end, d_counts, s);
 }
 
+int mg_screen_to_host(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
+                      int64_t win_begin, int64_t win_end, uint32_t* counts_out, void* stream) {
+    MG_CHECK_ARG(g && q && crit);
+    const size_t n2 = 2 * (size_t)q->n;
+    if (n2 == 0) return MG_OK;
+    MG_CHECK_ARG(counts_out != nullptr);
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t* d_counts = nullptr;
+    MG_CUDA(dev_alloc((void**)&d_counts, sizeof(uint32_t) * n2, s));
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n2, s);
+    int rc = e == cudaSuccess ? mg_screen(g, q, crit, pam, win_begin, win_end, d_counts, stream) : MG_ERR_CUDA;
+    if (rc == MG_OK) {
+        e = cudaMemcpyAsync(counts_out, d_counts, sizeof(uint32_t) * n2, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("screen failed: %s", cudaGetErrorString(e)); rc = MG_ERR_CUDA; }
+    } else if (e != cudaSuccess) {
+        set_error("clearing the counts failed: %s", cudaGetErrorString(e));
+    }
+    dev_free(d_counts, s);
+    return rc;
+}
+
 int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
                    const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
                    const char* grna, int n, int len, const mg_criteria* crit, const mg_pam* pam,
