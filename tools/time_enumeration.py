@@ -1,5 +1,11 @@
-import time, numpy as np, sys, os
-sys.path.insert(0, "/root/repo")
+"""Timing of the enumeration side (device PAM scan + host object build + writers) on an 8 Mb target: python tools/time_enumeration.py"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from minorg_b200 import _lib
 from minorg_b200.generate_grna import find_multi_gRNA
 from minorg_b200.pam import PAM
