@@ -245,7 +245,9 @@ class gRNAHits:
                 tlen = 0
             target = seq_targets.get(tid)
             if target is None:
-                target = dummy.setdefault((tid, tlen), Target("N" * int(tlen), id=tid, strand="+"))
+                target = dummy.get((tid, tlen))
+                if target is None:           # one dummy per (id, length): the reference builds an N-string per ROW
+                    target = dummy[(tid, tlen)] = Target("N" * int(tlen), id=tid, strand="+")
             hit = gRNAHit(target, int(start) - 1, int(end), strand, gid)
             hit.set_parent_sense(sense)
             self.add_hit(seq, hit)
