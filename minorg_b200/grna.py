@@ -158,6 +158,13 @@ class gRNAHits:
                 return s
         return None
 
+    def _index_by_id(self):
+        """{id: gRNASeq}, first occurrence wins like the linear search of get_gRNAseq_by_id (one pass for many ids)."""
+        out = {}
+        for s in self._gRNAseqs.values():
+            out.setdefault(s.id, s)
+        return out
+
     def flatten_gRNAseqs(self):
         return list(self._gRNAseqs.values())
 
@@ -190,7 +197,8 @@ class gRNAHits:
         if seqs:
             chosen = [self.get_gRNAseq_by_seq(s) for s in seqs]
         elif ids:
-            chosen = [self.get_gRNAseq_by_id(i) for i in ids]
+            by_id = self._index_by_id()
+            chosen = [by_id.get(i) for i in ids]
         else:
             chosen = self.flatten_gRNAseqs()
         groups = {}
@@ -263,7 +271,8 @@ class gRNAHits:
         elif seqs:
             chosen = [self.get_gRNAseq_by_seq(s) for s in seqs if self.get_gRNAseq_by_seq(s) is not None]
         elif ids:
-            chosen = [s for s in (self.get_gRNAseq_by_id(i) for i in ids) if s is not None]
+            by_id = self._index_by_id()
+            chosen = [by_id[i] for i in ids if i in by_id]
         else:
             open(fout, "w").close()
             return
