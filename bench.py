@@ -30,8 +30,12 @@ TARGET_LEN = 2000
 GRNA_LEN = 20
 MAX_MISMATCH = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size (8x135 Mb, N=1) scan launch, from the ncu capture
-# summarised in profiles/ (see DESIGN.md); algorithmic bytes are 2 query chunks x 405 MB genome + 34 MB of query tables
+# summarised in profiles/ (see DESIGN.md); algorithmic bytes are 2 query chunks x 405 MB genome + 34 MB of query tables.
+# The number is a CAPTURE, not measured in this run: the JSON names the file and the commit of the kernel it was taken on.
 NCU_DRAM_BYTES_PER_LAUNCH = 860234752   # profiles/r01_pairs_v3_fullsize_dram.csv: 843.68 MB read + 16.56 MB written
+NCU_DRAM_CAPTURE = {"file": "profiles/r01_pairs_v3_fullsize_dram.csv", "kernel_commit": "4de4244 (round 1; screen_pairs_kernel unchanged since)",
+                    "metric": "dram__bytes_read.sum + dram__bytes_write.sum, one N=1 full-size launch"}
+WINDOW_SHARD_HALO = 4096                 # chunk halo of the window-shard check: planted targets (masks) are 2 kb
 
 
 def parse_args():
@@ -46,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the gapped / pattern side measurements (N=1 only)")
+    ap.add_argument("--no-checks", action="store_true", help="skip the oracle parity slice and the window-shard check")
     ap.add_argument("--gapped", action="store_true",
                     help="NOT the BASELINE config: time the north star's <=4 mismatches / <=1 gap criterion on the same genomes "
                          "(edit-distance rows kernel + verifier); implies --no-cpu-baseline --no-other-modes")
@@ -188,25 +193,40 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_screen_rate(ascii_host, clens, grnas, seconds, threads):
-    """Times the C oracle (oracle/screen_oracle.c, 'port' of the reference criteria) on a bounded sample of
-    the workload: all gRNA x the first S bases of genome 0.  -> (gRNA*Gbp/s, sample description)."""
-    from oracle import c_oracle
-    c_oracle.build()
-    n = len(grnas)
+def counts_checksum(c):
+    """64-bit sum of counts[i] * (i + 1): equal at every N because the all-reduced count vector is."""
+    c = np.asarray(c, dtype=np.uint64)
+    w = np.arange(1, len(c) + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int((c * w).sum(dtype=np.uint64))
 
-    def run(nbases):
-        blob = ascii_host[:nbases]
-        off = np.array([0, nbases], dtype=np.int64)
-        t0 = time.perf_counter()
-        c_oracle.screen_hamming_arrays(blob, off, [], grnas, MAX_MISMATCH, threads=threads)
-        return time.perf_counter() - t0
-    probe = min(len(ascii_host), max(20000, 4000 * threads))
-    t = run(probe)
-    rate = probe / max(t, 1e-6)                      # bases/s for this gRNA set
-    nb = int(min(len(ascii_host), max(probe, rate * seconds)))
-    t = run(nb)
-    return n * nb / 1e9 / t, "%d gRNA x first %d bp of genome 0, <=%d mismatches, both strands, %.1f s" % (n, nb, MAX_MISMATCH, t)
+
+def sass_counts(kernel):
+    """Instruction counts of a shipped kernel's hot loop, from profiles/sass_counts.json (tools/sass_counts.py: cuobjdump
+    of the library, committed with the excerpt it was counted on)."""
+    with open(os.path.join(ROOT, "profiles", "sass_counts.json")) as f:
+        return json.load(f)["kernels"][kernel]
+
+
+def parity_slice(clens, seconds, rate_bases_per_s):
+    """Window range of genome 0 for the oracle comparison: the end of contig 0 and the start of contig 1 - so the slice
+    holds a contig boundary (windows hanging off both contig ends) - wide enough on one side to contain a whole planted,
+    masked target, and as large as the CPU time budget allows.  -> (A, B): windows of contig 0 that start in
+    [len0 - A, len0) and of contig 1 that start in [-L+1, B)."""
+    pos = plant_positions(0, clens)
+    end0 = [clens[0] - s for c, s in pos if c == 0]          # distance of a target's START from the end of contig 0
+    start1 = [s + TARGET_LEN for c, s in pos if c == 1]      # END of a target of contig 1
+    need_a = min(end0) + GRNA_LEN if end0 else None
+    need_b = min(start1) + GRNA_LEN if start1 else None
+    budget = int(max(200_000, rate_bases_per_s * seconds))
+    a = b = budget // 2
+    if need_a is not None and (need_b is None or need_a <= need_b):
+        a = max(a, need_a)
+        b = max(50_000, min(b, budget - a))
+    elif need_b is not None:
+        b = max(b, need_b)
+        a = max(50_000, min(a, budget - b))
+    return min(a, clens[0]), min(b, clens[1])
 
 
 def main():
@@ -312,12 +332,30 @@ def main():
     ms_per_step = total_ms / args.steps
     value = args.grna * total_bases / 1e9 / (ms_per_step / 1e3)
 
-    # sanity on the result itself (full-size property): every gRNA cut from a planted target hits random
-    # sequence ~835 times per 1.08 Gbp at <=4 mismatches; on-target copies are masked.
+    # the all-reduced per-query counts of the last timed step: identical at every N (same total work), and so is
+    # their checksum - SCALE runs prove multi-GPU correctness by printing one value at N = 1, 2, 4, 8
     n = len(grnas)
     steps_cnt, stage2 = _lib.last_screen_stats()
-    host_counts = (counts[:n] + counts[n:]).cpu().numpy()
+    counts_host = counts.cpu().numpy().astype(np.uint32)
+    host_counts = counts_host[:n].astype(np.int64) + counts_host[n:].astype(np.int64)
     fails = int((host_counts > 0).sum())
+    checksum = counts_checksum(counts_host)
+
+    # ---- checks that every bench run carries: counts against the CPU oracle on a slice of the full-size
+    # genome, and one genome cut into chunk + halo shards against the same genome screened whole
+    parity = None
+    shard_check = None
+    cpu_baseline = None
+    threads = len(os.sched_getaffinity(0))
+    if not args.no_checks:
+        if rank == 0 and not args.gapped:
+            want_baseline = world == 1 and not args.no_cpu_baseline
+            parity, cpu_baseline = parity_check(torch, _lib, genome, queries, crit, grnas, masks, ascii_dev, clens,
+                                                args.cpu_seconds if want_baseline else 3.0, threads, stream, device)
+            if not want_baseline:
+                cpu_baseline = None
+        shard_check = window_shard_check(torch, dist, _lib, rank, world, device, stream, queries, crit, grnas, clens,
+                                         targets_all, ascii_dev if 0 in my_genomes else None, masks if 0 in my_genomes else None)
 
     # ---- side measurements (N=1): the other criteria of the path on the same resident genomes, one timed pass each
     # after one warm-up pass.  Not the headline: the gapped line is the north star's <=4 mm / <=1 gap criterion.
@@ -377,93 +415,208 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e_ms = dt.item() * 1e3 / e_steps
-        assert np.array_equal(np.asarray(c, dtype=np.int64), host_counts.astype(np.int64)) or world > 1
+        # at every N: the (reduced) counts of the host-buffer path equal the resident path's
+        e2e_equal = bool(np.array_equal(np.asarray(c, dtype=np.int64), host_counts))
+        assert e2e_equal, "end-to-end counts differ from the resident-genome counts (world %d)" % world
         e2e = {"value": args.grna * total_bases / 1e9 / (e_ms / 1e3), "unit": "gRNA*Gbp/s", "ms_per_step": e_ms,
                "steps": e_steps, "h2d_bytes_per_step": int(len(harr) * world + gblob.nbytes * world),
-               "d2h_bytes_per_step": int(8 * n * world)}
-    else:
-        harr = None
+               "d2h_bytes_per_step": int(8 * n * world), "counts_equal_resident_path": e2e_equal}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (screen_bitsliced_kernel)
-    # The scan is bound by the shared-memory load pipe (LSU, one 32-bit load per lane per gRNA position per 32
-    # queries) and by the ALU pipe (LOP3 adders) at nearly the same level; HBM carries 0.375 B/base once per
-    # launch and is ~4 orders of magnitude below its roofline.  Denominators: mg_microbench measures both
-    # pipes on this GPU; the work per (warp, 32-query group) step is counted by the kernel itself
-    # (mg_last_screen_stats): every step loads/sums the first T1 positions, a fraction f2 the remaining L-T1.
+    # ---- roofline of the dominant kernel
+    # The scan is bound by the shared-memory load pipe (LSU) and by the ALU pipe (LOP3) at nearly the same level; HBM
+    # carries 0.375 B/base once per query chunk and is ~4 orders of magnitude below its roofline.  Denominators:
+    # mg_microbench measures both pipes on this GPU.  Work per (warp, 32-query group) step: instruction counts read from
+    # the SASS of the shipped kernel (profiles/sass_counts.json, tools/sass_counts.py) x the fraction of steps that go
+    # past the vote, counted by the kernel itself (mg_last_screen_stats).
     peaks, peaks_src = measured_peaks()
     lop3 = _lib.microbench(0, stream)     # Glane-ops/s, measured here
     lds = _lib.microbench(1, stream)
+    imad = _lib.microbench(7, stream)
+    both = _lib.microbench(8, stream)
+    int_peaks = {"lop3_glane_ops": lop3, "lds32_glane_ops": lds, "imad_glane_ops": imad, "lop3_imad_interleaved_glane_ops": both}
     my_bases = sum(clens) * len(my_genomes)
     cells_per_launch = 2.0 * n * my_bases
     achieved = cells_per_launch / (kern_ms / 1e3) / 1e12
-    # pair-word scan (screen_pairs_kernel<20,4>): stage 1 = 10 pair words per lane (shared memory) + 15 LOP3 (SASS); the
-    # fraction f2 of steps that survives the vote adds the exact count: 20 per-position words (global/L2) + ~60 ALU ops
-    t_pairs = 10
-    f2 = (stage2 / steps_cnt) if steps_cnt else 1.0
-    loads_per_step = t_pairs + f2 * GRNA_LEN
-    alu_per_step = 15.0 + f2 * 60.0
-    peak_lsu = lds * 1e9 * 32.0 / loads_per_step / 1e12
-    peak_alu = lop3 * 1e9 * 32.0 / alu_per_step / 1e12
-    peak = min(peak_lsu, peak_alu)
-    brute = lds * 1e9 * 32.0 / GRNA_LEN / 1e12
-    n_chunks = -(-((2 * n + 31) // 32) // 352)     # 352 query groups of pair tables fit one SM's shared memory
-    alg_bytes = my_bases * 0.375 * n_chunks   # packed genome (2-bit bases + 1-bit invalid plane) streamed once per query chunk
     if args.gapped:
-        # gapped_rows_kernel<20,20>: 170 issue slots per (32 gRNA, text character) (SASS: 82 ALU + 82 FMA + 5 LSU), one
-        # slot per scheduler and cycle; only the N gRNA-orientation queries of a strand pass take part, two passes
-        f_hz = (clocks or {}).get("sm_mhz", 1965.0) * 1e6
-        peak_rows = sms * 4 * f_hz * 32.0 * 32.0 / 170.0 / 1e12
-        roofline = {"bound": "issue slots (ALU 82 + FMA 82 + LSU 5 instructions per character and 32 gRNA)", "achieved": achieved,
+        # gapped_rows_kernel<20,20>: issue slots per (32 gRNA, text character) from the SASS of the per-character loop, less
+        # the cold survivor path; one slot per scheduler and cycle = the measured LOP3+IMAD interleaved rate
+        sc = sass_counts("gapped_rows_kernel<20,20>")["per_character"]
+        slots = sc.get("LOP3", 0) + sc.get("IMAD", 0) + sc.get("LDS", 0) + sc.get("SHF", 0) + 4      # + loop control
+        peak_rows = both * 1e9 * 32.0 / slots / 1e12
+        roofline = {"bound": "issue slots (ALU + FMA pipes together)", "achieved": achieved,
                     "peak": peak_rows, "unit": "Tcell/s", "frac": achieved / peak_rows, "traffic": None,
+                    "issue_slots_per_character_and_group": slots, "sass": "profiles/r02_sass_gapped_rows_L20_char_loop.txt",
+                    "peak_source": "mg_microbench 8 on this GPU: LOP3 and IMAD interleaved %.0f Glane-op/s" % both,
                     "kernel": "gapped_rows_kernel<20,20> + verify_kernel", "kernel_ms": kern_ms,
                     "note": "achieved includes the verifier pass over the edit-distance survivors (8e-5 of the cells)"}
         out = {"metric": "gRNA x Gbp screened/sec (exhaustive, device-timed)", "value": value, "unit": "gRNA*Gbp/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bit-sliced 2-bit bases)",
                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": None,
-               "roofline": roofline, "cpu_baseline": None, "device": name,
+               "roofline": roofline, "cpu_baseline": None, "device": name, "int_peaks": int_peaks,
                "cells_per_s": 2.0 * args.grna * total_bases / (ms_per_step / 1e3), "grna_failed": fails,
+               "counts_checksum": "0x%016x" % checksum, "counts_total": int(host_counts.sum()),
+               "parity_check": parity, "window_shard_check": shard_check,
                "side_measurement": "north-star criterion (<=4 mm / <=1 gap), not BASELINE.json's bench config"}
         print(json.dumps(out))
         if world > 1:
             dist.destroy_process_group()
         return 0
+    kname = "screen_pairs_kernel<%d,%d,1024,0>" % (GRNA_LEN, MAX_MISMATCH)
+    sc = sass_counts(kname)
+    s1, s2 = sc["stage1_hot_path"], sc["stage2_fall_through"]
+    f2 = (stage2 / steps_cnt) if steps_cnt else 1.0
+    loads_per_step = s1["LDS"] + f2 * s2.get("LDG", 0)
+    alu2 = sum(v for k, v in s2.items() if k in ("LOP3", "IADD3", "VIADD", "SHF", "PRMT", "ISETP", "MOV"))
+    alu_per_step = s1["LOP3"] + f2 * alu2
+    peak_lsu = lds * 1e9 * 32.0 / loads_per_step / 1e12
+    peak_alu = lop3 * 1e9 * 32.0 / alu_per_step / 1e12
+    peak = min(peak_lsu, peak_alu)
+    brute = lds * 1e9 * 32.0 / GRNA_LEN / 1e12
+    n_chunks = -(-((2 * n + 31) // 32) // 352)     # 352 query groups of pair tables fit one SM's shared memory
+    alg_bytes = my_bases * 0.375 * n_chunks   # packed genome (2-bit bases + 1-bit invalid plane) streamed once per query chunk
     roofline = {"bound": "lsu(shared-memory loads)" if peak_lsu <= peak_alu else "alu(lop3)", "achieved": achieved,
                 "peak": peak, "unit": "Tcell/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.genome_mb == 135.0 and world == 1) else None,
-                "traffic_source": "profiles/r01_pairs_v3_fullsize_dram.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, N=1 full-size launch)",
+                "traffic_source": NCU_DRAM_CAPTURE,
                 "peak_source": "mg_microbench on this GPU: LOP3 %.0f Glane-op/s, LDS.32 %.0f Glane-op/s" % (lop3, lds),
-                "work_per_step": {"second_stage_fraction": f2, "lds_per_lane": loads_per_step, "alu_per_lane": alu_per_step},
+                "work_per_step": {"second_stage_fraction": f2, "lds_per_lane": loads_per_step, "alu_per_lane": alu_per_step,
+                                  "source": "profiles/sass_counts.json (cuobjdump of the shipped library): stage 1 %d LDS + %d LOP3, "
+                                            "stage 2 %d LDG + %d ALU-pipe instructions" % (s1["LDS"], s1["LOP3"], s2.get("LDG", 0), alu2)},
                 "ceilings_tcell_s": {"lsu_shared": peak_lsu, "alu_lop3": peak_alu, "lsu_without_early_out": brute},
                 "frac_of_ceiling_without_early_out": achieved / brute,
-                "kernel": "screen_pairs_kernel<20,4,1024>", "kernel_ms": kern_ms,
+                "kernel": kname, "kernel_ms": kern_ms,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_gbs": alg_bytes / (kern_ms / 1e3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "peak_source": peaks_src,
                         "note": "0.375 B/base once per query chunk: HBM is ~3 orders below its roofline; the scan is integer-pipe bound"}}
 
-    cpu_baseline = None
-    if not args.no_cpu_baseline and harr is not None:
-        threads = len(os.sched_getaffinity(0))
-        v, sample = cpu_screen_rate(harr[:sum(clens)], clens, grnas, args.cpu_seconds, threads)
-        cpu_baseline = {"value": v, "unit": "gRNA*Gbp/s", "cores": threads, "kind": "port", "sample": sample}
-
     out = {"metric": "gRNA x Gbp screened/sec (exhaustive, device-timed)", "value": value, "unit": "gRNA*Gbp/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bit-sliced 2-bit bases)",
            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * world,
-           "roofline": roofline, "cpu_baseline": cpu_baseline, "device": name,
+           "roofline": roofline, "cpu_baseline": cpu_baseline, "device": name, "int_peaks": int_peaks,
            "cells_per_s": 2.0 * args.grna * total_bases / (ms_per_step / 1e3), "grna_failed": fails,
+           "counts_checksum": "0x%016x" % checksum, "counts_total": int(host_counts.sum()),
+           "parity_check": parity, "window_shard_check": shard_check,
            "other_modes": other_modes}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def parity_check(torch, _lib, genome, queries, crit, grnas, masks, ascii_dev, clens, seconds, threads, stream, device):
+    """Device counts on a window range of the FULL-SIZE resident genome 0 against oracle/screen_oracle.c on the same
+    windows: the end of contig 0 + the start of contig 1 (a contig boundary with windows hanging off both ends) reaching
+    past a planted, masked target that the gRNA were cut from.  The oracle run doubles as the cpu_baseline sample.
+    -> (parity_check dict, cpu_baseline dict)."""
+    from oracle import c_oracle
+    c_oracle.build()
+    n = len(grnas)
+    len0, len1 = clens[0], clens[1]
+    host = ascii_dev[:len0 + len1].cpu().numpy()
+    off = np.array([0, len0, len0 + len1], dtype=np.int64)
+    m01 = [(c, s, e) for c, s, e in masks if c < 2]
+    probe = min(len0, 40000)
+    t0 = time.perf_counter()
+    c_oracle.screen_hamming_arrays(host, off, m01, grnas, MAX_MISMATCH, threads, [(0, probe), (0, 0)])
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    a, b = parity_slice(clens, seconds, rate)
+    ranges = [(len0 - a, len0), (-GRNA_LEN, b)]
+    t0 = time.perf_counter()
+    want = c_oracle.screen_hamming_arrays(host, off, m01, grnas, MAX_MISMATCH, threads, ranges).astype(np.int64)
+    cpu_s = time.perf_counter() - t0
+    wb = genome.contig_global_start(0) + len0 - a
+    we = genome.contig_global_start(1) + b
+    c = torch.zeros(2 * n, dtype=torch.int32, device=device)
+    _lib.screen(genome, queries, crit, None, c.data_ptr(), win_begin=wb, win_end=we, stream=stream)
+    torch.cuda.synchronize()
+    got = (c[:n] + c[n:]).cpu().numpy().astype(np.int64)
+    equal = bool(np.array_equal(got, want))
+    in_slice = [(c_, s, e) for c_, s, e in m01 if (c_ == 0 and s >= len0 - a) or (c_ == 1 and e <= b)]
+    window_bp = a + b + GRNA_LEN - 1
+    parity = {"window_bp": int(window_bp), "n_grna": n, "equal": equal,
+              "windows": "genome 0: contig 0 starts [%d, %d) + contig 1 starts [%d, %d): one contig boundary" % (len0 - a, len0, -GRNA_LEN + 1, b),
+              "masked_targets_in_slice": len(in_slice), "max_mismatch": MAX_MISMATCH,
+              "counts_total": int(want.sum()), "grna_with_hits": int((want > 0).sum()),
+              "oracle": "oracle/screen_oracle.c oracle_screen_hamming_win, %d threads, %.1f s" % (threads, cpu_s)}
+    if not equal:
+        bad = np.nonzero(got != want)[0]
+        parity["first_differences"] = [(int(i), int(got[i]), int(want[i])) for i in bad[:5]]
+    cpu = {"value": n * window_bp / 1e9 / cpu_s, "unit": "gRNA*Gbp/s", "cores": threads, "kind": "port",
+           "sample": "%d gRNA x %d bp of genome 0 around the contig 0/1 boundary (masks applied), <=%d mismatches, both strands, %.1f s; "
+                     "the same slice is the parity_check" % (n, window_bp, MAX_MISMATCH, cpu_s)}
+    assert equal, "parity_check: device counts differ from the CPU oracle: %s" % parity.get("first_differences")
+    return parity, cpu
+
+
+def window_shard_check(torch, dist, _lib, rank, world, device, stream, queries, crit, grnas, clens, targets_all, ascii0, masks_full):
+    """Genome 0 cut into chunk + halo shards (mg_genome_from_device_ascii_chunk; one per rank, or 4 on one GPU when N=1):
+    every shard packs only its own bases, finds the planted targets that START in its range, the mask lists are gathered,
+    every shard screens the windows it owns, counts are summed (all-reduce) and compared on rank 0 with genome 0
+    screened whole.  This is how BASELINE configs[4] (one 3.1 Gb genome over 8 GPUs) runs."""
+    from minorg_b200.distributed import shard_windows
+    n = len(grnas)
+    parts = world if world > 1 else 4
+    if ascii0 is None:
+        ascii0 = synth_genome_device(torch, 0, clens, targets_all[0], device)
+    else:
+        ascii0 = ascii0[:sum(clens)]
+    off0 = np.concatenate([[0], np.cumsum(clens)]).astype(np.int64)
+    names0 = ["g0_c%d" % c for c in range(len(clens))]
+    glen0 = _lib.layout_global_length(off0)
+    mask_seqs0 = [sq for _, sq in targets_all[0]]
+    mine = list(range(parts)) if world == 1 else [rank]
+    chunks, found = [], []
+    for r in mine:
+        wb, we = shard_windows(glen0, GRNA_LEN, r, parts)
+        g = _lib.Genome.from_device_ascii_chunk(ascii0.data_ptr(), off0, names0, wb, we, halo=WINDOW_SHARD_HALO, stream=stream)
+        found += [(c, s, e) for _, c, s, e, _ in g.find_exact(mask_seqs0, stream=stream)]
+        chunks.append(g)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, found)
+        found = [m for part in gathered for m in part]
+    masks0 = sorted(set(found))
+    total = torch.zeros(2 * n, dtype=torch.int32, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for g in chunks:
+        g.set_masks(masks0, stream=stream)
+    torch.cuda.synchronize()
+    e0.record()
+    for g in chunks:
+        _lib.screen(g, queries, crit, None, total.data_ptr(), stream=stream)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    chunk_bytes = [g.device_bytes for g in chunks]
+    for g in chunks:
+        g.free()
+    if rank != 0:
+        return None
+    whole = _lib.Genome.from_device_ascii(ascii0.data_ptr(), off0, names0, stream=stream)
+    ref_masks = sorted({(c, s, e) for c, s, e in masks_full if c < len(clens)})
+    whole.set_masks(ref_masks, stream=stream)
+    ref = torch.zeros(2 * n, dtype=torch.int32, device=device)
+    _lib.screen(whole, queries, crit, None, ref.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    equal = bool(torch.equal(ref, total))
+    masks_equal = masks0 == ref_masks
+    out = {"genome": "genome 0 (%d bp, %d contigs)" % (sum(clens), len(clens)), "shards": parts,
+           "ranks": world, "halo_bp": WINDOW_SHARD_HALO, "equal": equal, "masks_equal": masks_equal,
+           "masks_found_by_shards": len(masks0), "ms": ms, "counts_total": int(ref.sum().item()),
+           "shard_device_bytes": int(max(chunk_bytes)), "whole_genome_device_bytes": int(whole.device_bytes)}
+    whole.free()
+    assert equal and masks_equal, "window-shard check failed: %s" % out
+    return out
 
 
 def reference_arm(args, clens, config):
@@ -510,7 +663,8 @@ def reference_arm(args, clens, config):
             times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
     value = len(grnas) * nb / 1e9 / sec
-    sample = "%d gRNA x %d bp synthetic sample per step, %d threads" % (len(grnas), nb, threads)
+    sample = ("%d gRNA x %d bp per step, %d threads; NOT the GPU arm's inputs: an independent uniform random sample (seed 0) "
+              "with no planted targets and no masks, gRNA enumerated by the oracle's own NGG scan" % (len(grnas), nb, threads))
     out = {"impl": "reference", "metric": "gRNA x Gbp screened/sec (exhaustive, device-timed)", "value": value,
            "unit": "gRNA*Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -72,6 +72,21 @@ int mg_genome_from_fasta(const char* path, int threads, void* stream, mg_genome*
 /* Same, with the ASCII bytes already on the device (synthetic-genome benchmarks). */
 int mg_genome_from_device_ascii(const char* d_seq, const int64_t* offsets, int n_contigs, void* stream,
                                 mg_genome** out);
+/* Chunk of a subject for one GPU of several (BASELINE.json north_star: "genomes are sharded by chunk (with gRNA-length
+ * halo) across the 8 GPUs").  The coordinate space is the WHOLE subject's - seq/offsets/n_contigs
+ * describe all of it, and contigs, masks and window ranges keep their global meaning - but only the bases of global
+ * positions [chunk_begin - halo, chunk_end + halo) are copied to the device and packed.  The handle owns the windows
+ * whose first base lies in [chunk_begin, chunk_end): mg_screen and mg_mask_find restrict themselves to them, so the
+ * chunks of a partition of [0, mg_layout_global_length()) evaluate every cell (and report every mask occurrence)
+ * exactly once.  halo >= 256 and >= the longest mask sequence + 64 when mg_mask_find is used.  The reference has no
+ * counterpart: it hands whole FASTA files to blastn processes (MINORg.py:2182-2195). */
+int64_t mg_layout_global_length(const int64_t* offsets, int n_contigs);   /* global length of the layout, no device work */
+int mg_genome_from_ascii_chunk(const char* seq, const int64_t* offsets, int n_contigs, int64_t chunk_begin,
+                               int64_t chunk_end, int64_t halo, void* stream, mg_genome** out);
+int mg_genome_from_device_ascii_chunk(const char* d_seq, const int64_t* offsets, int n_contigs, int64_t chunk_begin,
+                                      int64_t chunk_end, int64_t halo, void* stream, mg_genome** out);
+/* owned window range and stored base range (global coordinates); any pointer may be NULL */
+int mg_genome_owned_range(const mg_genome* g, int64_t* begin, int64_t* end, int64_t* stored_begin, int64_t* stored_end);
 int mg_genome_n_contigs(const mg_genome* g);
 int64_t mg_genome_contig_length(const mg_genome* g, int contig);
 int64_t mg_genome_total_bases(const mg_genome* g);    /* sum of contig lengths (no padding) */
@@ -206,7 +221,9 @@ int mg_last_screen_stats(uint64_t* out /* [2] */);
 
 /* Integer-pipe microbenchmarks used for the roofline denominators of the scan kernel (bench.py):
  * which: 0 = LOP3 (ALU pipe) lane-ops, 1 = shared-memory 32-bit loads (LSU), 2 / 3 = 64- / 128-bit shared-memory
- * loads with the scan's broadcast pattern (4 adjacent entries per warp).  Returns G lane-instructions/s in *gops. */
+ * loads with the scan's broadcast pattern (4 adjacent entries per warp), 4 = indexed constant-bank loads, 5 / 6 = warp
+ * shuffles alone / interleaved 1:1 with shared loads, 7 = IMAD (FMA pipe), 8 = IMAD and LOP3 interleaved 1:1 (both integer
+ * pipes together: the issue-slot ceiling of the gapped rows kernel).  Returns G lane-instructions/s in *gops. */
 int mg_microbench(int which, double* gops, void* stream);
 
 #ifdef __cplusplus

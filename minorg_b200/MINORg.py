@@ -102,6 +102,8 @@ class MINORg:
         self.exclude = None
         self.masked = {}
         self._genomes = {}
+        self._genome_halo = {}
+        self._window_mode = None      # (rank, world) while one subject file is split over the ranks by chunk + halo
         # Not a reference attribute.  False (default): every cell of every subject is evaluated and the per-gRNA COUNTS are
         # exact (what bench.py and the parity tests measure).  True: filter_background only needs pass/fail, so each
         # subject is screened in window slices and a gRNA that already has an off-target leaves the query set - same
@@ -221,13 +223,29 @@ class MINORg:
             self.write_all_grna_eqv()
 
     # ---- sub-command: filter (background) ------------------------------------------------------
-    def _genome(self, fname):
-        """Packed genome of a FASTA file, resident in HBM (cached per file): (handle, contig names)."""
+    def _genome(self, fname, halo=256):
+        """Packed genome of a FASTA file, resident in HBM (cached per file): (handle, contig names).
+        In window mode (one subject split over the ranks of a torch.distributed job, self._window_mode = (rank, world))
+        the handle is this rank's CHUNK of the file: the bases of its window range plus `halo` on both sides."""
         fname = _fname(fname)
-        if fname not in self._genomes:
-            genome = _lib.Genome.from_fasta(fname)      # native reader (host threads) + H2D + 2-bit pack
-            self._genomes[fname] = (genome, genome.names)
-        return self._genomes[fname]
+        halo = max(256, int(halo))
+        cached = self._genomes.get(fname)
+        if cached is not None and self._window_mode is not None and self._genome_halo.get(fname, 0) < halo:
+            cached[0].free()                            # a longer mask sequence needs a wider halo
+            cached = None
+        if cached is None:
+            if self._window_mode is None:
+                genome = _lib.Genome.from_fasta(fname)  # native reader (host threads; plain or gzip) + H2D + 2-bit pack
+            else:
+                rank, world = self._window_mode
+                blob, offsets, names = _lib.read_fasta_native(fname)
+                begin, end = _dist.shard_windows(_lib.layout_global_length(offsets), 1, rank, world)
+                genome = _lib.Genome.from_host_array_chunk(blob, offsets, names, begin, end, halo=halo)
+                self._genome_halo[fname] = halo
+            if genome.n_contigs == 0:                   # an empty subject would pass every gRNA: refuse it
+                raise MINORgError("%s holds no sequence records" % fname)
+            cached = self._genomes[fname] = (genome, genome.names)
+        return cached
 
     @staticmethod
     def _ranks():
@@ -255,17 +273,25 @@ class MINORg:
         for mf in mask_fnames:
             if mf:
                 seqs.extend(fasta_to_dict(mf).items())
-        plain = [(i, s) for i, s in seqs if s and set(s) <= set("ACGTacgt")]
-        other = [(i, s) for i, s in seqs if s and not set(s) <= set("ACGTacgt")]
+        # filter_grna.py:71: U/u count as standard bases and go down the BLAST path, where U pairs with T
+        standard = set("ACGTUacgtu")
+        plain = [(i, s.replace("U", "T").replace("u", "t")) for i, s in seqs if s and set(s) <= standard]
+        other = [(i, s) for i, s in seqs if s and not set(s) <= standard]
+        halo = 64 + max([len(s) for _, s in plain] or [0])   # a chunk reports the occurrences that START in its range
         for group in self._subject_groups():
             for fname in group.values():
                 if fname in self.masked:
                     continue
-                genome, names = self._genome(fname)
+                genome, names = self._genome(fname, halo=halo)
                 found = set()
                 if plain:
                     for si, ci, start, end, _strand in genome.find_exact([s for _, s in plain]):
                         found.add(Masked(plain[si][0], names[ci], start, end))
+                if self._window_mode is not None:       # every rank needs every mask: an interval may span a cut
+                    import torch.distributed as dist
+                    parts = [None] * self._window_mode[1]
+                    dist.all_gather_object(parts, sorted((m.masked, m.molecule, m.start, m.end) for m in found))
+                    found = {Masked(*t) for part in parts for t in part}
                 if other:
                     found.update(_find_identical_host(other, read_fasta(fname)))
                 self.masked[fname] = tuple(found)
@@ -305,11 +331,14 @@ class MINORg:
         stream = 0
         for length, idx in by_len.items():
             pam = PAM(self.pam, length).program() if not self.ot_pamless else None
-            wb, we = (0, -1) if windows is None else _dist.shard_windows(genome.global_length, length, *windows)
-            if windows is not None and we <= wb:
+            own_b, own_e = genome.owned_range[:2]
+            if windows is None or (own_b, own_e) != (0, genome.global_length):
+                wb, we = own_b, own_e                   # whole genome, or this rank's chunk (mg_screen clips to it anyway)
+            else:
+                wb, we = _dist.shard_windows(genome.global_length, length, *windows)   # whole genome resident: range only
+            we = min(we, max(0, genome.global_length - length + 1))
+            if we <= wb:
                 continue
-            if we < 0:
-                we = max(0, genome.global_length - length + 1)
             crit = self._criteria(length)
             # exact counts: one pass.  verdicts only: geometric window slices, survivors only carry on
             n_slices = 12 if self.screen_verdicts_only else 1
@@ -345,18 +374,30 @@ class MINORg:
             raise MINORgError("MINORg.filter_background requires gRNA (generated with self.grna())")
         if self.grna_fasta is None:
             self.write_all_grna_fasta()
-        print("Masking on-targets")
-        self._mask_ontargets(self.target, *([self.ref_gene] if (mask_reference and self.genes and self.ref_gene) else []),
-                             *self.mask, *other_mask_fnames)
-        if self._ranks()[0] == 0:
-            self.write_mask_report(self.results_fname("masked.txt"))
-        print("Finding off-targets")
         ref, query, bg = self._subject_groups()
         files = []
         for enabled, group in (((self.screen_reference or self.query_reference) and ref, ref), (query, query), (bg, bg)):
             if enabled:
                 files += [f for f in group.values() if f not in files]      # a file is screened once (:2188)
         rank, world = self._ranks()
+        # fewer subject files than ranks: every file is cut into one chunk (+ halo) per rank instead of dealing files
+        all_files = {f for group in (ref, query, bg) for f in group.values()}
+        window_mode = (rank, world) if (world > 1 and len(files) < world and all_files == set(files)) else None
+        if window_mode != self._window_mode:
+            self._free_genomes()
+            self._window_mode = window_mode
+        print("Masking on-targets")
+        if mask_reference and self.genes and not self.ref_gene:
+            # the reference derives the gene sequences from its annotation here (MINORg.py:2168-2171); this build has no
+            # GFF handling, so the caller must supply them - silently skipping the masks would fail valid gRNA
+            import warnings
+            warnings.warn("mask_reference=True with self.genes set but no self.ref_gene FASTA: the reference genes are "
+                          "NOT masked (supply their sequences via ref_gene= or mask=)", RuntimeWarning, stacklevel=2)
+        self._mask_ontargets(self.target, *([self.ref_gene] if (mask_reference and self.genes and self.ref_gene) else []),
+                             *self.mask, *other_mask_fnames)
+        if self._ranks()[0] == 0:
+            self.write_mask_report(self.results_fname("masked.txt"))
+        print("Finding off-targets")
         if world == 1:
             excl = set()
             for fname in files:
@@ -367,7 +408,7 @@ class MINORg:
             import torch
             ids_seqs = list(fasta_to_dict(self.grna_fasta).items())
             total = np.zeros(len(ids_seqs), dtype=np.int64)
-            if len(files) >= world:
+            if self._window_mode is None and len(files) >= world:
                 for fname in _dist.shard_files(files, rank, world):
                     total += self.offtarget_counts(fname, [s for _, s in ids_seqs])
             else:
@@ -444,7 +485,11 @@ class MINORg:
         print("\n%d mutually exclusive gRNA set(s) requested. %d set(s) found." % (sets, len(grna_sets)))
         return grna_sets
 
-    def close(self):
+    def _free_genomes(self):
         for g, _ in self._genomes.values():
             g.free()
         self._genomes = {}
+        self._genome_halo = {}
+
+    def close(self):
+        self._free_genomes()

@@ -29,6 +29,7 @@ EXPORTS = [
     "mg_microbench", "mg_last_screen_stats",
     "mg_fasta_read", "mg_fasta_n_records", "mg_fasta_name", "mg_fasta_offsets", "mg_fasta_sequence", "mg_fasta_free",
     "mg_genome_from_fasta", "mg_screen_to_host",
+    "mg_layout_global_length", "mg_genome_from_ascii_chunk", "mg_genome_from_device_ascii_chunk", "mg_genome_owned_range",
 ]
 
 
@@ -76,6 +77,11 @@ def lib():
     L.mg_init.argtypes = [C.c_int, C.c_char_p, C.c_int, i32p]
     L.mg_genome_from_ascii.argtypes = [vp, i64p, C.c_int, vp, C.POINTER(vp)]
     L.mg_genome_from_device_ascii.argtypes = [vp, i64p, C.c_int, vp, C.POINTER(vp)]
+    L.mg_layout_global_length.argtypes = [i64p, C.c_int]
+    L.mg_layout_global_length.restype = C.c_int64
+    L.mg_genome_from_ascii_chunk.argtypes = [vp, i64p, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, C.POINTER(vp)]
+    L.mg_genome_from_device_ascii_chunk.argtypes = [vp, i64p, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, C.POINTER(vp)]
+    L.mg_genome_owned_range.argtypes = [vp, i64p, i64p, i64p, i64p]
     L.mg_genome_n_contigs.argtypes = [vp]
     L.mg_genome_contig_length.argtypes = [vp, C.c_int]
     L.mg_genome_contig_length.restype = C.c_int64
@@ -153,6 +159,16 @@ def read_fasta_native(path, threads=0):
     return blob, offsets, names
 
 
+def layout_global_length(offsets):
+    """Global length (bases, incl. padding) of the device layout of contigs with these offsets - what
+    distributed.shard_windows needs to cut a subject into chunks before any rank has packed anything."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    r = int(lib().mg_layout_global_length(_i64(offsets), len(offsets) - 1))
+    if r < 0:
+        raise MinorgB200Error("invalid contig offsets")
+    return r
+
+
 def init(device=0):
     name = C.create_string_buffer(256)
     sms = C.c_int32(0)
@@ -193,6 +209,32 @@ class Genome:
         check(lib().mg_genome_from_ascii(_ptr(arr), _i64(offsets), len(offsets) - 1, C.c_void_p(stream), C.byref(h)),
               "mg_genome_from_ascii")
         return cls(h.value, names)
+
+    @classmethod
+    def from_host_array_chunk(cls, arr, offsets, names, chunk_begin, chunk_end, halo=256, stream=0):
+        """One rank's chunk of a subject (mg_genome_from_ascii_chunk): arr/offsets describe the WHOLE subject, only the
+        bases of global positions [chunk_begin - halo, chunk_end + halo) cross PCIe; coordinates stay global."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        h = C.c_void_p()
+        check(lib().mg_genome_from_ascii_chunk(_ptr(arr), _i64(offsets), len(offsets) - 1, int(chunk_begin), int(chunk_end),
+                                               int(halo), C.c_void_p(stream), C.byref(h)), "mg_genome_from_ascii_chunk")
+        return cls(h.value, names)
+
+    @classmethod
+    def from_device_ascii_chunk(cls, dptr, offsets, names, chunk_begin, chunk_end, halo=256, stream=0):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        h = C.c_void_p()
+        check(lib().mg_genome_from_device_ascii_chunk(C.c_void_p(dptr), _i64(offsets), len(offsets) - 1, int(chunk_begin),
+                                                      int(chunk_end), int(halo), C.c_void_p(stream), C.byref(h)),
+              "mg_genome_from_device_ascii_chunk")
+        return cls(h.value, names)
+
+    @property
+    def owned_range(self):
+        """(own_begin, own_end, stored_begin, stored_end) in global coordinates."""
+        v = [C.c_int64(0) for _ in range(4)]
+        check(lib().mg_genome_owned_range(self.handle, *[C.byref(x) for x in v]), "mg_genome_owned_range")
+        return tuple(int(x.value) for x in v)
 
     @classmethod
     def from_fasta(cls, path, threads=0, stream=0):

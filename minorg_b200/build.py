@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
     if force or procs or _stale(LIB, objs):
-        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-lz"])
     return LIB
 
 

@@ -2,6 +2,7 @@
 #include <ctime>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 #include "common.cuh"
 
@@ -27,6 +28,28 @@ __global__ void __launch_bounds__(1024, 1) ubench_lop3(uint32_t* out, int iters)
             asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(f) : "r"(g), "r"(h));
             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(a));
             asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(h) : "r"(a), "r"(b));
+        }
+    }
+    if ((a ^ b ^ c ^ d ^ e ^ f ^ g ^ h) == 0x12345u) out[0] = a;
+}
+
+// IMAD (FMA pipe; the gapped rows kernel moves 4 of its 7 word operations per DP cell there) alone (MIX = 0) and
+// interleaved 1:1 with LOP3 (MIX = 1: the two pipes together = the issue-slot ceiling of the rows kernel).
+template <int MIX>
+__global__ void __launch_bounds__(1024, 1) ubench_imad(uint32_t* out, int iters, uint32_t one) {
+    uint32_t a = threadIdx.x * 2654435761u, b = blockIdx.x * 40503u + 1u, c = a ^ 0x9E3779B9u, d = b + 77u;
+    uint32_t e = a + 1, f = b + 2, g = c + 3, h = d + 4;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(one), "r"(b));
+            if (MIX) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(e) : "r"(f), "r"(g));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b) : "r"(one), "r"(c));
+            if (MIX) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(f) : "r"(g), "r"(h));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(c) : "r"(one), "r"(d));
+            if (MIX) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(e));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(one), "r"(a));
+            if (MIX) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(h) : "r"(e), "r"(f));
         }
     }
     if ((a ^ b ^ c ^ d ^ e ^ f ^ g ^ h) == 0x12345u) out[0] = a;
@@ -131,7 +154,7 @@ int mg_last_screen_stats(uint64_t* out) {
 }
 
 int mg_microbench(int which, double* gops, void* stream) {
-    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 6);
+    MG_CHECK_ARG(gops != nullptr && which >= 0 && which <= 8);
     cudaStream_t s = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     MG_CUDA(cudaGetDevice(&dev));
@@ -151,12 +174,14 @@ int mg_microbench(int which, double* gops, void* stream) {
         else if (which == 3) ubench_lds_wide<4><<<sms, 1024, 0, s>>>(d, iters);
         else if (which == 4) ubench_ldc<<<sms, 1024, 0, s>>>(d, iters);
         else if (which == 5) ubench_shfl<0><<<sms, 1024, 0, s>>>(d, iters);
-        else ubench_shfl<1><<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 6) ubench_shfl<1><<<sms, 1024, 0, s>>>(d, iters);
+        else if (which == 7) ubench_imad<0><<<sms, 1024, 0, s>>>(d, iters, 1u);
+        else ubench_imad<1><<<sms, 1024, 0, s>>>(d, iters, 1u);
         MG_CUDA(cudaEventRecord(e1, s));
         MG_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
         MG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : which == 1 ? 32.0 : which == 6 ? 32.0 : 16.0);   // load/shuffle INSTRUCTIONS per lane
+        const double ops = (double)sms * 1024.0 * iters * (which == 0 ? 64.0 : which == 1 ? 32.0 : which == 6 ? 32.0 : which == 7 ? 32.0 : which == 8 ? 64.0 : 16.0);   // INSTRUCTIONS per lane and iteration
         const double r = ops / (ms * 1e-3) / 1e9;
         if (rep > 0 && r > best) best = r;
     }
@@ -176,8 +201,13 @@ int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, 
     const int64_t last = g->glen - L;            // buffers carry spare words beyond glen
     if (win_begin < 0) win_begin = 0;
     if (win_end < 0 || win_end > last + 1) win_end = last + 1;
+    if (g->is_chunk) {                           // a chunk only owns (and only stores the bases of) its own window range
+        win_begin = std::max(win_begin, g->own_begin);
+        win_end = std::min(win_end, g->own_end);
+    }
     if (win_end <= win_begin || q->n == 0) return MG_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    g->last_stream = s;
     const bool fast = crit->n_units == 0 && crit->max_gap == 0 && crit->pamless;
     if (fast) {
         if (crit->max_mismatch >= L) { set_error("mismatch budget %d >= gRNA length %d", crit->max_mismatch, L); return MG_ERR_ARG; }
@@ -215,14 +245,36 @@ int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
     MG_CHECK_ARG(counts_out != nullptr || n == 0);
     MG_CHECK_ARG(offsets != nullptr && n_contigs >= 0 && n_masks >= 0);
     cudaStream_t s = (cudaStream_t)stream;
-    mg_queries* q = nullptr;
     uint32_t* d_counts = nullptr;
     const bool trace = getenv("MG_TRACE") != nullptr;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t0 = now();
-    int rc = mg_queries_create(grna, n, len, stream, &q);
+    // Per-thread cache across calls: a pipeline screens the same gRNA set against one subject after another
+    // (MINORg.filter_background: reference, query and background files), so the query tables, the copy stream and the
+    // count scratch of the previous call are kept; the gRNA bytes are compared, not trusted by pointer.
+    struct HostCache {
+        int device = -1, n = 0, len = 0;
+        std::string blob;
+        mg_queries* q = nullptr;
+        cudaStream_t cs = nullptr;
+        ~HostCache() {}                      // released with the context at process exit
+    };
+    static thread_local HostCache cache;
+    int dev = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    int rc = MG_OK;
+    const size_t gbytes = (size_t)std::max(n, 0) * (size_t)std::max(len, 0);
+    const bool hit = cache.q != nullptr && cache.device == dev && cache.n == n && cache.len == len &&
+                     cache.blob.size() == gbytes && (gbytes == 0 || memcmp(cache.blob.data(), grna, gbytes) == 0);
+    if (!hit) {
+        if (cache.q) { mg_queries_free(cache.q); cache.q = nullptr; }
+        rc = mg_queries_create(grna, n, len, stream, &cache.q);
+        if (rc == MG_OK) { cache.device = dev; cache.n = n; cache.len = len; cache.blob.assign(grna ? grna : "", gbytes); }
+        else cache.q = nullptr;
+    }
+    mg_queries* q = cache.q;
     if (rc == MG_OK && n > 0) {
-        if (cudaMalloc(&d_counts, sizeof(uint32_t) * 2 * (size_t)n) != cudaSuccess) { set_error("cudaMalloc(counts) failed"); rc = MG_ERR_NOMEM; }
+        if (dev_alloc((void**)&d_counts, sizeof(uint32_t) * 2 * (size_t)n, s) != cudaSuccess) { set_error("allocating the counts failed"); rc = MG_ERR_NOMEM; }
         else cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * 2 * (size_t)n, s);
     }
     // Contigs are independent (no window spans two), so the subject goes through in batches of whole contigs: batch i+1
@@ -231,8 +283,8 @@ int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
     const int64_t total = n_contigs ? offsets[n_contigs] - offsets[0] : 0;
     const int64_t batch_bases = std::max<int64_t>(total / 8, (int64_t)32 << 20);
     std::vector<mg_genome*> batches;
-    cudaStream_t cs = nullptr;
-    if (rc == MG_OK && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); rc = MG_ERR_CUDA; }
+    if (rc == MG_OK && cache.cs == nullptr && cudaStreamCreateWithFlags(&cache.cs, cudaStreamNonBlocking) != cudaSuccess) { cache.cs = nullptr; set_error("cudaStreamCreate failed"); rc = MG_ERR_CUDA; }
+    cudaStream_t cs = cache.cs;
     double t_copy = 0.0;
     for (int c0 = 0; rc == MG_OK && (c0 < n_contigs || (n_contigs == 0 && batches.empty())); ) {
         int c1 = c0;
@@ -263,10 +315,8 @@ int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
         cudaStreamSynchronize(s);
     }
     const double t3 = now();
-    cudaFree(d_counts);
-    mg_queries_free(q);
+    dev_free(d_counts, s);
     for (mg_genome* g : batches) mg_genome_free(g);
-    if (cs) cudaStreamDestroy(cs);
     if (trace) fprintf(stderr, "[mg_screen_host] %d batches; host time in H2D+pack+masks %.1f ms (overlaps the screen), total %.1f ms, free %.1f ms\n",
                        (int)batches.size(), t_copy, t3 - t0, now() - t3);
     return rc;

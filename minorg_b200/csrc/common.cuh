@@ -38,6 +38,7 @@ void dev_free(void* p, cudaStream_t s);
 constexpr int kPad = 64;        // invalid bases between contigs (>= L + gaps + PAM flank)
 constexpr int kAlign = 32;      // contig global starts are multiples of this (one invalid-plane word)
 constexpr int kCodeInvalid = 4;
+constexpr int kMinHalo = 256;   // smallest halo of a chunk genome: gRNA + gaps + PAM flank + the 48-base window loads
 
 // What the kernels see of a genome.
 struct GenomeView {
@@ -118,9 +119,17 @@ struct mg_genome {
     int64_t* d_mend_pm = nullptr;
     int n_masks = 0;
     size_t bases_words = 0, invalid_words = 0;
+    // A CHUNK of a subject (mg_genome_from_*_chunk): the coordinate space is the whole subject's, but the planes only
+    // hold the global range [lo, hi) = the owned window range [own_begin, own_end) plus a halo on both sides.  The
+    // kernels index the planes with global positions through pointers biased by lo (multiple of 128 bases).
+    int64_t lo = 0, hi = 0;                     // stored global range (whole genome: [0, glen))
+    int64_t own_begin = 0, own_end = 0;         // window starts this handle owns (whole genome: [0, glen))
+    int64_t halo = 0;
+    bool is_chunk = false;
+    mutable cudaStream_t last_stream = nullptr; // stream of the most recent screen: the planes are freed in its order
     mg::GenomeView view() const {
         mg::GenomeView v;
-        v.bases = d_bases; v.invalid = d_invalid; v.glen = glen; v.cstart = d_cstart; v.cend = d_cend;
+        v.bases = d_bases - (lo >> 4); v.invalid = d_invalid - (lo >> 5); v.glen = glen; v.cstart = d_cstart; v.cend = d_cend;
         v.n_contigs = n_contigs; v.mstart = d_mstart; v.mend_pm = d_mend_pm; v.n_masks = n_masks;
         return v;
     }
@@ -132,6 +141,7 @@ struct mg_queries {
     uint32_t* d_tab = nullptr;
     uint32_t* d_tab2 = nullptr;
     uint4* d_packed = nullptr;
+    cudaStream_t stream = nullptr;          // the creating stream; the tables are freed in its order
     mg::QueriesView view() const {
         mg::QueriesView v;
         v.codes = d_codes; v.tab = d_tab; v.tab2 = d_tab2; v.packed = d_packed; v.n = n; v.len = len; v.n_groups = n_groups;

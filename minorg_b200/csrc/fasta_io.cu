@@ -7,8 +7,11 @@
 // Record semantics (identical to minorg_b200.fasta.read_fasta_arrays, checked byte for byte in tests/test_host_mirror.py):
 // a header line is a line whose first byte is '>'; the record id is the first whitespace-delimited token of the header;
 // the sequence is every byte up to the next header line except '\n', '\r', ' ' and '\t', case preserved; bytes before
-// the first header are ignored.  Plain files only (gzip stays with the Python reader).
+// the first header are ignored.  gzip files (magic 1f 8b; the subjects MINORg users keep are often .fasta.gz) are
+// inflated with zlib first.  mg_genome_from_fasta refuses a file without a single record: a subject with no contigs
+// would let every gRNA pass the background check.
 #include <fcntl.h>
+#include <zlib.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -156,7 +159,29 @@ int mg_fasta_read(const char* path, int threads, mg_fasta** out) {
         void* map = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (map == MAP_FAILED) { close(fd); delete f; set_error("cannot map %s: %s", path, strerror(errno)); return MG_ERR_ARG; }
         madvise(map, (size_t)size, MADV_SEQUENTIAL);
-        rc = fasta_parse((const char*)map, size, threads, f);
+        const unsigned char* m = (const unsigned char*)map;
+        if (size >= 2 && m[0] == 0x1f && m[1] == 0x8b) {
+            // gzip: inflate the whole file (multi-member files included) into a host buffer, then parse that
+            std::vector<char> plain;
+            gzFile gz = gzopen(path, "rb");
+            if (!gz) { rc = MG_ERR_ARG; set_error("cannot open %s as gzip", path); }
+            else {
+                gzbuffer(gz, 1 << 20);
+                size_t used = 0;
+                plain.resize((size_t)std::max<int64_t>(size * 4, 1 << 20));
+                for (;;) {
+                    if (plain.size() - used < (1u << 20)) plain.resize(plain.size() * 2);
+                    const int got = gzread(gz, plain.data() + used, (unsigned)std::min<size_t>(plain.size() - used, 1u << 30));
+                    if (got < 0) { int en = 0; set_error("gzip error in %s: %s", path, gzerror(gz, &en)); rc = MG_ERR_ARG; break; }
+                    if (got == 0) break;
+                    used += (size_t)got;
+                }
+                gzclose(gz);
+                if (rc == MG_OK) rc = fasta_parse(plain.data(), (int64_t)used, threads, f);
+            }
+        } else {
+            rc = fasta_parse((const char*)map, size, threads, f);
+        }
         munmap(map, (size_t)size);
     }
     close(fd);
@@ -175,6 +200,11 @@ int mg_genome_from_fasta(const char* path, int threads, void* stream, mg_genome*
     mg_fasta* f = nullptr;
     int rc = mg_fasta_read(path, threads, &f);
     if (rc != MG_OK) return rc;
+    if (f->names.empty()) {      // a subject without contigs would let every gRNA pass the background check
+        mg_fasta_free(f);
+        set_error("%s holds no FASTA record (no line starts with '>'): not a FASTA file?", path);
+        return MG_ERR_ARG;
+    }
     rc = mg_genome_from_ascii(f->seq, f->offsets.data(), (int)f->names.size(), stream, out);
     if (rc != MG_OK || fasta_out == nullptr) mg_fasta_free(f);
     else *fasta_out = f;

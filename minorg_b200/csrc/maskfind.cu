@@ -20,11 +20,11 @@ constexpr int kSeedChunk = 1024;
 
 __global__ void __launch_bounds__(256)
 maskfind_kernel(GenomeView gv, const Seed* __restrict__ seeds, int n_seeds, const uint8_t* __restrict__ codes,
-                int64_t cap, int32_t* out_seed, int64_t* out_pos, unsigned long long* counter) {
+                int64_t p_begin, int64_t p_end, int64_t cap, int32_t* out_seed, int64_t* out_pos, unsigned long long* counter) {
     __shared__ Seed sh[kSeedChunk];
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = p_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t lo = 0, hi = 0, inv = 0xFFFFFFFFu;
-    const bool active = p < gv.glen;
+    const bool active = p < p_end;
     if (active) load_window(gv, p, lo, hi, inv);
     for (int base = 0; base < n_seeds; base += kSeedChunk) {
         const int m = min(kSeedChunk, n_seeds - base);
@@ -68,6 +68,10 @@ extern "C" int mg_mask_find(const mg_genome* g, const char* seqs, const int64_t*
         const int64_t len = b - a;
         if (len <= 0) continue;
         MG_CHECK_ARG(len < ((int64_t)1 << 30));
+        if (g->is_chunk && len + 64 > g->halo) {      // an occurrence starting in the owned range must end inside the stored one
+            set_error("mask sequence %d (%lld bases) is longer than the chunk's halo (%lld): build the chunk with halo >= longest mask + 64", i, (long long)len, (long long)g->halo);
+            return MG_ERR_ARG;
+        }
         std::vector<uint8_t> fwd((size_t)len);
         bool plain = true;
         for (int64_t k = 0; k < len; ++k) { const int c = code_of(seqs[a + k]); if (c < 0) { plain = false; break; } fwd[(size_t)k] = (uint8_t)c; }
@@ -106,8 +110,10 @@ extern "C" int mg_mask_find(const mg_genome* g, const char* seqs, const int64_t*
         cudaMemcpyAsync(d_seeds, seeds.data(), sizeof(Seed) * seeds.size(), cudaMemcpyHostToDevice, s);
         cudaMemcpyAsync(d_codes, codes.data(), codes.size(), cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(d_cnt, 0, 8, s);
-        const unsigned grid = (unsigned)((g->glen + 255) / 256);
-        maskfind_kernel<<<grid, 256, 0, s>>>(g->view(), d_seeds, (int)seeds.size(), d_codes, cap, d_oseed, d_opos, d_cnt);
+        // a chunk reports the occurrences that START in its owned range (each occurrence has exactly one owner)
+        const int64_t pb = g->own_begin, pe = std::min(g->own_end, g->glen);
+        const unsigned grid = (unsigned)((std::max<int64_t>(pe - pb, 0) + 255) / 256);
+        if (grid) maskfind_kernel<<<grid, 256, 0, s>>>(g->view(), d_seeds, (int)seeds.size(), d_codes, pb, pe, cap, d_oseed, d_opos, d_cnt);
         unsigned long long cnt = 0;
         if ((e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) { fail("D2H"); break; }
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { fail("maskfind kernel"); break; }

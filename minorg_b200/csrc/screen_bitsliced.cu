@@ -324,12 +324,25 @@ static int launch_popc(const mg_genome* g, const mg_queries* q, int k, int64_t w
 }
 
 // [0] (warp, query-group) steps, [1] steps that needed the second stage - of the most recent launch
-static unsigned long long* g_stats = nullptr;
+// One buffer per device (a process may screen on several devices; the counters must live on the launching one).
+constexpr int kMaxDevices = 64;
+static unsigned long long* g_stats_dev[kMaxDevices] = {nullptr};
+
+static int stats_buffer(unsigned long long** out) {
+    int dev = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { *out = nullptr; return MG_OK; }     // no statistics beyond 64 devices
+    if (!g_stats_dev[dev]) MG_CUDA(cudaMalloc(&g_stats_dev[dev], 16));
+    *out = g_stats_dev[dev];
+    return MG_OK;
+}
 
 int screen_stats(unsigned long long out[2]) {
     out[0] = out[1] = 0;
-    if (!g_stats) return MG_OK;
-    MG_CUDA(cudaMemcpy(out, g_stats, 16, cudaMemcpyDeviceToHost));
+    int dev = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || !g_stats_dev[dev]) return MG_OK;
+    MG_CUDA(cudaMemcpy(out, g_stats_dev[dev], 16, cudaMemcpyDeviceToHost));
     return MG_OK;
 }
 
@@ -353,9 +366,10 @@ static int launch_one(const mg_genome* g, const mg_queries* q, int kthr, int64_t
     int64_t grid = (nwin + THREADS - 1) / THREADS;
     if (grid > sms) grid = sms;             // persistent: one CTA per SM, each owns a contiguous genome slice
     if (grid < 1) grid = 1;
-    if (!g_stats) MG_CUDA(cudaMalloc(&g_stats, 16));
-    MG_CUDA(cudaMemsetAsync(g_stats, 0, 16, s));
-    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts, gctx, g_stats);
+    unsigned long long* stats = nullptr;
+    { const int rc = stats_buffer(&stats); if (rc != MG_OK) return rc; }
+    if (stats) MG_CUDA(cudaMemsetAsync(stats, 0, 16, s));
+    kern<<<(unsigned)grid, THREADS, smem, s>>>(g->view(), q->view(), kthr, gpc, wb, we, d_counts, gctx, stats);
     MG_CUDA(cudaGetLastError());
     return MG_OK;
 }

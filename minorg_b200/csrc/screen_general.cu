@@ -8,6 +8,7 @@
 //   verifier   verify.cuh: exact enumeration of the alignment universe at the surviving anchors.
 // K = max_mismatch + max_gap without a pattern (MINORg.py:2037-2038: unaligned positions and gaps spend one
 // combined budget), or the bound the host derives from the pattern (ot_regex.OffTargetExpression.edit_bound).
+#include <algorithm>
 #include <chrono>
 #include "common.cuh"
 #include "verify.cuh"
@@ -83,10 +84,10 @@ myers_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, 
 // looking at four words before the drop instead of three measures the same).  A gap after (before) the
 // matching range moves the alignment's virtual end by at most Gp, so 2*Gp+1 anchors go to the exact verifier.
 constexpr int kPieceThreads = 1024;
-constexpr int kPieceMax = 16;          // positions of a piece that are compared (a longer piece is cut: still necessary)
 constexpr int kPieceLookups = 9;       // 16 positions: at most 7 pair words + 2 single words
 
 struct PieceOp {
+    int piece;                         // index of the piece in the criteria
     int minus;                         // 1: the reverse-complement queries (mirrored range)
     int n;                             // lookups
     int pair[kPieceLookups];           // 1: idx = pair index (positions 2 idx, 2 idx + 1); 0: idx = position
@@ -94,8 +95,11 @@ struct PieceOp {
 };
 
 // cold path: the queries of group word `hit` (already restricted to the op's orientation) survive at window p
+// An anchor is only queued if the window that owns it (e - L on '+', glen - e on '-') lies in [own_a, own_b): the scan
+// itself covers Gp extra windows on both sides, so every anchor of the shard is reached and none of a neighbour's is.
+// The tag (piece, offset) lets the verifier count an anchor that several (piece, window) pairs reach exactly once.
 static __device__ __noinline__ void emit_piece_hits(const GeneralCtx* __restrict__ ctx, uint32_t hit, int q0, int N, int L,
-                                                    int64_t p, int64_t glen) {
+                                                    int64_t p, int64_t glen, int piece, int64_t own_a, int64_t own_b) {
     const int Gp = ctx->Gp;
     while (hit) {
         const int i = __ffs(hit) - 1;
@@ -103,14 +107,17 @@ static __device__ __noinline__ void emit_piece_hits(const GeneralCtx* __restrict
         const int q = q0 + i;
         if (q >= 2 * N) continue;
         const int64_t e0 = q < N ? p + L : glen - p;
-        for (int d = -Gp; d <= Gp; ++d) emit_candidate(*ctx, q, e0 + d);
+        for (int d = -Gp; d <= Gp; ++d) {
+            const int64_t pw = q < N ? p + d : p - d;            // window owning anchor e0 + d
+            if (pw >= own_a && pw < own_b) emit_candidate(*ctx, q, e0 + d, kCandTagged | (piece << 8) | (d + Gp));
+        }
     }
 }
 
 template <int T, int EE>
 __global__ void __launch_bounds__(kPieceThreads, 1)
 pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx, PieceOp op, int groups_per_chunk, int64_t wb,
-              int64_t we) {
+              int64_t we, int64_t own_a, int64_t own_b) {
     extern __shared__ uint32_t tab[];                      // per group: pair table, then single-position table
     const int L = qv.len, N = qv.n, NPL = (L + 1) / 2;
     const int S2 = 16 * NPL + 1, S1 = 4 * L + 1, SG = S2 + S1;
@@ -154,7 +161,7 @@ pieces_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx,
                 if (q0 + 32 <= N) plus_bits = 0xFFFFFFFFu;
                 else if (q0 < N) plus_bits = (1u << (N - q0)) - 1u;
                 hit &= op.minus ? ~plus_bits : plus_bits;
-                if (hit) emit_piece_hits(ctx, hit, q0, N, L, p, gv.glen);
+                if (hit) emit_piece_hits(ctx, hit, q0, N, L, p, gv.glen, op.piece, own_a, own_b);
             };
             const char* t = reinterpret_cast<const char*>(tab);
             int g = 0;
@@ -202,7 +209,7 @@ static PieceOp make_piece_op(int a, int n, int minus) {
 }
 
 static int launch_pieces(const mg_genome* g, const mg_queries* q, const GeneralCtx* d_ctx, const PieceOp& op, int sms, int smem_max,
-                         int64_t a, int64_t b, cudaStream_t s) {
+                         int64_t a, int64_t b, int64_t own_a, int64_t own_b, cudaStream_t s) {
     const int L = q->len, SG = 16 * ((L + 1) / 2) + 1 + 4 * L + 1;
     const int max_groups = (smem_max - 1024) / (SG * 4);
     const int gpc = q->n_groups < max_groups ? q->n_groups : max_groups;
@@ -212,7 +219,7 @@ static int launch_pieces(const mg_genome* g, const mg_queries* q, const GeneralC
     switch (op.n) {
 #define MG_PIECES(TT) case TT: \
         MG_CUDA(cudaFuncSetAttribute(pieces_kernel<TT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pieces_kernel<TT, 3><<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, op, gpc, a, b); break;
+        pieces_kernel<TT, 3><<<(unsigned)grid, kPieceThreads, smem, s>>>(g->view(), q->view(), d_ctx, op, gpc, a, b, own_a, own_b); break;
         MG_PIECES(1) MG_PIECES(2) MG_PIECES(3) MG_PIECES(4) MG_PIECES(5) MG_PIECES(6) MG_PIECES(7) MG_PIECES(8) MG_PIECES(9)
 #undef MG_PIECES
         default: set_error("piece with %d lookups", op.n); return MG_ERR_ARG;
@@ -229,6 +236,27 @@ verify_kernel(GenomeView gv, QueriesView qv, const GeneralCtx* __restrict__ ctx,
     if (i >= n_cand) return;
     const Cand c = ctx->cand[i];
     const int gi = c.q < qv.n ? c.q : c.q - qv.n;
+    if (c.tag & kCandTagged) {
+        // exact-piece prefilter: the same anchor is reached from up to (pieces x (2 Gp + 1)) (piece, window) pairs.  It is
+        // counted by the first pair in (piece, offset) order whose piece matches - every pair's window is scanned by the
+        // launch that owns the anchor, so exactly one queued copy passes this test.
+        const int L = qv.len, Gp = ctx->Gp;
+        const int my_piece = (c.tag >> 8) & 0xFF, my_d = (c.tag & 0xFF) - Gp;
+        const bool plus = c.q < qv.n;
+        const uint8_t* codes = qv.codes + (size_t)c.q * L;               // oriented query (rows N.. are reverse complements)
+        for (int k = 0; k <= my_piece; ++k) {
+            const int pa = plus ? ctx->piece_start[k] : L - ctx->piece_start[k] - ctx->piece_len[k];
+            const int pn = min(ctx->piece_len[k], kPieceMax);
+            for (int d = -Gp; d <= Gp; ++d) {
+                if (k == my_piece && d >= my_d) break;
+                const int64_t pw = plus ? c.e - d - L : gv.glen - c.e + d;   // the window whose hit of piece k reaches anchor e with offset d
+                if (pw < 0 || pw > gv.glen - L) continue;
+                bool same = true;
+                for (int j = pa; j < pa + pn && same; ++j) same = codes[j] < 4 && base_at(gv, pw + j) == (int)codes[j];
+                if (same) return;                                         // an earlier pair owns this anchor
+            }
+        }
+    }
     if (verify_anchor(gv, *ctx, qv.codes + (size_t)gi * qv.len, qv.packed + gi, c.q < qv.n ? 1 : -1, c.e)) atomicAdd(counts + c.q, 1u);
 }
 
@@ -294,6 +322,8 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         for (int j = a; j < a + n; ++j) r |= 1u << (L - 1 - j);      // the same bases in a reverse-complemented query
         h.piece_fwd[k] = m;
         h.piece_rev[k] = r;
+        h.piece_start[k] = a;
+        h.piece_len[k] = n;
     }
     // candidate queue between the prefilter and the verifier pass
     h.cand_cap = 64ull << 20;                                   // 1 GB of 16-byte entries
@@ -302,8 +332,11 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         if (v >= 8) h.cand_cap = (unsigned long long)v;
     }
     MG_CUDA(dev_alloc((void**)&h.cand, sizeof(Cand) * h.cand_cap, s));
-    MG_CUDA(dev_alloc((void**)&h.cand_count, 8, s));
-    MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
+    if (dev_alloc((void**)&h.cand_count, 8, s) != cudaSuccess || cudaMemsetAsync(h.cand_count, 0, 8, s) != cudaSuccess) {
+        dev_free(h.cand, s); dev_free(h.cand_count, s);
+        set_error("candidate counter: %s", cudaGetErrorString(cudaGetLastError()));
+        return MG_ERR_NOMEM;
+    }
     int K = crit->n_units ? crit->prefilter_edits : crit->max_mismatch + crit->max_gap;
     if (K >= L) K = -1;
     const char* pf_env = getenv("MG_PREFILTER");        // "none": hand EVERY anchor to the verifier (tests: prefilter soundness)
@@ -312,9 +345,10 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
     // exceeds the host-proved bound, before the exhaustive walk (not in the soundness-test mode, which must not rely on it)
     h.edit_bound = (crit->n_units > 0 && crit->max_gap >= 1 && K >= 0 && !no_prefilter) ? K : -1;
     GeneralCtx* d_ctx = nullptr;
-    MG_CUDA(cudaMalloc(&d_ctx, sizeof h));
     int rc = MG_OK;
-    cudaError_t e = cudaMemcpyAsync(d_ctx, &h, sizeof h, cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaMalloc(&d_ctx, sizeof h);
+    if (e != cudaSuccess) { dev_free(h.cand, s); dev_free(h.cand_count, s); set_error("criteria buffer: %s", cudaGetErrorString(e)); return MG_ERR_NOMEM; }
+    e = cudaMemcpyAsync(d_ctx, &h, sizeof h, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);     // h is on this stack frame
     if (e != cudaSuccess) { cudaFree(d_ctx); dev_free(h.cand, s); dev_free(h.cand_count, s); set_error("copying criteria: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
 
@@ -341,8 +375,11 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             for (int k = 0; k < h.n_pieces; ++k)
                 for (int minus = 0; minus < 2; ++minus) {
                     const int pa = crit->piece_start[k], pn = crit->piece_len[k];
-                    const PieceOp op = make_piece_op(minus ? L - pa - pn : pa, pn, minus);
-                    const int r2 = launch_pieces(g, q, d_ctx, op, sms, smem_max, a, b, s);
+                    PieceOp op = make_piece_op(minus ? L - pa - pn : pa, pn, minus);
+                    op.piece = k;
+                    // Gp extra windows on both sides: an anchor of [a, b) may only be reachable from a neighbour's piece hit
+                    const int64_t sa = std::max<int64_t>(0, a - crit->max_gap), sb = std::min<int64_t>(g->glen - L + 1, b + crit->max_gap);
+                    const int r2 = launch_pieces(g, q, d_ctx, op, sms, smem_max, sa, sb, a, b, s);
                     if (r2 != MG_OK) return r2;
                 }
             return MG_OK;
@@ -406,7 +443,7 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
         const Slice r = todo.back();
         todo.pop_back();
         if (r.b <= r.a || r.g1 <= r.g0) continue;
-        MG_CUDA(cudaMemsetAsync(h.cand_count, 0, 8, s));
+        if ((e = cudaMemsetAsync(h.cand_count, 0, 8, s)) != cudaSuccess) break;      // falls through to the common clean-up
         const double t0 = trace ? now() : 0.0;
         rc = prefilter(r.a, r.b, r.g0, r.g1);
         if (rc != MG_OK) break;

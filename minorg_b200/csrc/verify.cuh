@@ -35,6 +35,7 @@ struct GeneralCtx {
     int32_t edit_bound;       // >= 0: host-proved bound of a gapped pattern (true => mm + gaps + unaligned <= this); -1: none
     int32_t n_pieces;         // exact-piece prefilter: position masks in gRNA orientation and mirrored (rc queries)
     uint32_t piece_fwd[MG_MAX_PIECES], piece_rev[MG_MAX_PIECES];
+    int32_t piece_start[MG_MAX_PIECES], piece_len[MG_MAX_PIECES];   // the same ranges as (start, length) in gRNA orientation
     // prefilter survivors are queued here and verified by a second kernel with one thread per candidate
     // (verifying inline would run one lane of a warp at a time and drag a 2 KB stack into the scan kernel)
     struct Cand* cand;
@@ -44,9 +45,11 @@ struct GeneralCtx {
 
 struct Cand {
     int32_t q;        // oriented query index: q < N = gRNA q on '+', q >= N = gRNA q-N on '-'
-    int32_t pad;
+    int32_t tag;      // 0, or kCandTagged | piece << 8 | (offset + Gp): which (piece, offset) of the exact-piece prefilter queued it
     int64_t e;        // anchor: virtual end of the alignment in strand coordinates
 };
+constexpr int32_t kCandTagged = 1 << 16;
+constexpr int kPieceMax = 16;          // positions of a piece that are compared (a longer piece is cut: still necessary)
 
 // Python slice [start:end:step] with concrete bounds on a sequence of n elements; step = +1 if end >= start
 // else -1 (blast.py:140-147).  Visits indices first, first+step, ... while (step > 0 ? i < last : i > last).
@@ -609,9 +612,9 @@ namespace mg {
 
 // Hand a prefilter survivor to the verifier pass.  The counter keeps counting past the capacity: the host sees
 // the overflow, learns the survivor density from it and re-runs the range in slices that fit.
-__device__ __forceinline__ void emit_candidate(const GeneralCtx& c, int q, int64_t e) {
+__device__ __forceinline__ void emit_candidate(const GeneralCtx& c, int q, int64_t e, int32_t tag = 0) {
     const unsigned long long slot = atomicAdd(c.cand_count, 1ull);
-    if (slot < c.cand_cap) c.cand[slot] = Cand{q, 0, e};
+    if (slot < c.cand_cap) c.cand[slot] = Cand{q, tag, e};
 }
 
 }  // namespace mg

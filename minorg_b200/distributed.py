@@ -1,5 +1,5 @@
 """Multi-GPU plumbing for the screen: one process per GPU (torch.distributed, NCCL over NVLink), work split by
-genome file or - for one large genome - by window range, and ONE all-reduce of the per-gRNA counts.
+genome file or - for one large genome - by chunk (+ halo) of the window range, and ONE all-reduce of the per-gRNA counts.
 
 The reference's only parallelism is a process pool over genome FILES (functions.py:76-100, MINORg.py:2182-2195);
 cells are independent, so the only exchange step is the reduction of per-gRNA results."""
@@ -12,9 +12,11 @@ def shard_files(items, rank, world):
 
 
 def shard_windows(global_length, grna_len, rank, world):
-    """Window-start range [begin, end) owned by `rank` when ONE packed genome (resident on every GPU: 0.375
-    B/base, 1.2 GB for a 3.1 Gbp genome) is split by chunk.  A window belongs to the shard holding its first
-    base; because every rank holds the whole packed genome the gRNA-length halo needs no exchange."""
+    """Window-start range [begin, end) owned by `rank` when ONE subject is split by chunk.  A window belongs to the
+    shard holding its first base.  Each rank packs only its range plus a halo (mg_genome_from_ascii_chunk: gRNA length +
+    gaps + PAM flank, or the longest mask sequence for the mask finder), so nothing is exchanged but the per-gRNA counts;
+    global_length comes from _lib.layout_global_length(offsets) before anything is on a device.  (With the whole
+    packed genome resident on every GPU the same ranges work through mg_screen's win_begin/win_end.)"""
     n_windows = max(0, int(global_length) - int(grna_len) + 1)
     per = -(-n_windows // world)
     per = -(-per // 32) * 32                      # warp-aligned cuts

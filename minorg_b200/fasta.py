@@ -12,10 +12,21 @@ def reverse_complement(seq):
     return bytes(seq).translate(_COMPLEMENT)[::-1]
 
 
+def _open(path):
+    """Binary handle on a FASTA file, transparently inflating gzip (magic 1f 8b)."""
+    fh = open(path, "rb")
+    magic = fh.read(2)
+    fh.seek(0)
+    if magic == b"\x1f\x8b":
+        import gzip
+        return gzip.open(fh, "rb")
+    return fh
+
+
 def read_fasta(path):
     """-> [(id, sequence str)] in file order (duplicate ids are kept, like SeqIO.parse)."""
     records, name, parts = [], None, []
-    with open(path, "rb") as fh:
+    with _open(path) as fh:
         for raw in fh:
             if raw[:1] == b">":
                 if name is not None:
@@ -57,7 +68,8 @@ def read_fasta_arrays(path):
     """Whole-genome reader for the device path: -> (uint8 array of the concatenated sequence bytes, int64
     offsets[n+1], names).  Same record semantics as read_fasta (id = first header token, whitespace removed,
     case preserved) but vectorised with numpy: a 1 Gbp FASTA never becomes a Python str."""
-    raw = np.fromfile(path, dtype=np.uint8)
+    with _open(path) as fh:
+        raw = np.frombuffer(fh.read(), dtype=np.uint8)
     if raw.size == 0:
         return np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.int64), []
     line_starts = np.concatenate(([0], np.flatnonzero(raw == 10) + 1))

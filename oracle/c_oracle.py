@@ -37,7 +37,8 @@ def screen_hamming(contigs, masks, grnas, max_mismatch, threads=1):
     return screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads)
 
 
-def screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads=1):
+def screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads=1, win_ranges=None):
+    """win_ranges (optional): per contig (lo, hi) - only windows whose start lies in [lo, hi) are counted."""
     masks = list(masks)
     mc = np.array([m[0] for m in masks] or [0], dtype=np.int32)
     ms = np.array([m[1] for m in masks] or [0], dtype=np.int64)
@@ -47,9 +48,15 @@ def screen_hamming_arrays(blob, offsets, masks, grnas, max_mismatch, threads=1):
     gb = np.frombuffer(b"".join(g) or b"\0", dtype=np.uint8)
     out = np.zeros(max(1, len(g)), dtype=np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = _load().oracle_screen_hamming(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
-                                       C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
-                                       C.c_int(threads), p(out))
+    if win_ranges is None:
+        lo = hi = None
+    else:
+        lo = np.array([r[0] for r in win_ranges], dtype=np.int64)
+        hi = np.array([r[1] for r in win_ranges], dtype=np.int64)
+        assert len(lo) == len(offsets) - 1
+    rc = _load().oracle_screen_hamming_win(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
+                                           C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
+                                           C.c_int(threads), p(out), None if lo is None else p(lo), None if hi is None else p(hi))
     if rc != 0:
         raise RuntimeError("oracle_screen_hamming failed: %d" % rc)
     return out[:len(g)]

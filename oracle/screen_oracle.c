@@ -75,10 +75,26 @@ static void* run(void* arg) {
     return NULL;
 }
 
-/* counts_out[i] = number of (window, strand) pairs within budget and outside masks, over all contigs. */
+/* counts_out[i] = number of (window, strand) pairs within budget and outside masks, over all contigs.
+ * win_lo / win_hi (NULL = every window): per contig, only the windows whose START lies in [win_lo[c], win_hi[c])
+ * are counted (clipped to [-L+1, len)) - the C side of mg_screen's window shards, used by bench.py's parity check on
+ * a slice of a full-size genome. */
+int oracle_screen_hamming_win(const char* seq, const int64_t* offsets, int n_contigs,
+                              const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                              const char* grna, int n, int L, int max_mm, int n_threads, uint32_t* counts_out,
+                              const int64_t* win_lo, const int64_t* win_hi);
+
 int oracle_screen_hamming(const char* seq, const int64_t* offsets, int n_contigs,
                           const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
                           const char* grna, int n, int L, int max_mm, int n_threads, uint32_t* counts_out) {
+    return oracle_screen_hamming_win(seq, offsets, n_contigs, mask_contig, mask_start, mask_end, n_masks, grna, n, L, max_mm,
+                                     n_threads, counts_out, NULL, NULL);
+}
+
+int oracle_screen_hamming_win(const char* seq, const int64_t* offsets, int n_contigs,
+                              const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                              const char* grna, int n, int L, int max_mm, int n_threads, uint32_t* counts_out,
+                              const int64_t* win_lo, const int64_t* win_hi) {
     if (L < 1 || L > 32 || n < 0 || n_threads < 1) return -2;
     const int nq = 2 * n;
     uint64_t* qbits = (uint64_t*)calloc((size_t)nq + 1, 8);
@@ -96,13 +112,18 @@ int oracle_screen_hamming(const char* seq, const int64_t* offsets, int n_contigs
     uint32_t* priv = (uint32_t*)calloc((size_t)n_threads * (size_t)(nq + 1), 4);
     for (int c = 0; c < n_contigs; ++c) {
         const int64_t len = offsets[c + 1] - offsets[c];
-        uint8_t* codes = (uint8_t*)malloc((size_t)len + 1);
-        for (int64_t i = 0; i < len; ++i) codes[i] = (uint8_t)code_of(seq[offsets[c] + i]);
         int nm = 0;
         int64_t* ms = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
         int64_t* me = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
         for (int i = 0; i < n_masks; ++i) if (mask_contig[i] == c) { ms[nm] = mask_start[i]; me[nm] = mask_end[i]; ++nm; }
-        const int64_t first = -(int64_t)L + 1, last = len; /* window starts [first, last) */
+        int64_t first = -(int64_t)L + 1, last = len; /* window starts [first, last) */
+        if (win_lo != NULL && win_hi != NULL) {
+            if (win_lo[c] > first) first = win_lo[c];
+            if (win_hi[c] < last) last = win_hi[c];
+            if (last <= first) { free(ms); free(me); continue; }
+        }
+        uint8_t* codes = (uint8_t*)malloc((size_t)len + 1);
+        for (int64_t i = 0; i < len; ++i) codes[i] = (uint8_t)code_of(seq[offsets[c] + i]);
         const int64_t total = last - first;
         for (int t = 0; t < n_threads; ++t) {
             job_t* j = &jobs[t];

@@ -404,6 +404,20 @@ def test_native_fasta_reader_matches_python_reader(tmp_path):
             assert got[2] == want[2] and np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), fixture
     with pytest.raises(_lib.MinorgB200Error):
         _lib.read_fasta_native(str(tmp_path / "does_not_exist.fa"))
+    # gzip (magic 1f 8b) is inflated by both readers; the repo's config-1 subjects ship that way
+    import gzip
+    from minorg_b200.fasta import read_fasta
+    for name in ("crlf", "long_lines", "big"):
+        gz = tmp_path / (name + ".fa.gz")
+        with gzip.open(gz, "wb") as fh:
+            fh.write(cases[name].encode("latin-1"))
+        want, got, py = read_fasta_arrays(str(tmp_path / (name + ".fa"))), _lib.read_fasta_native(str(gz)), read_fasta_arrays(str(gz))
+        for r in (got, py):
+            assert r[2] == want[2] and np.array_equal(r[1], want[1]) and np.array_equal(r[0][:int(want[1][-1])], want[0][:int(want[1][-1])]), name
+        assert read_fasta(str(gz)) == read_fasta(str(tmp_path / (name + ".fa")))
+    cfg = os.path.join(here, "golden", "config1", "subset_9654.fasta.gz")
+    got = _lib.read_fasta_native(cfg)
+    assert len(got[2]) == 8 and int(got[1][-1]) == 161377
 
 
 def test_map_reader_matches_reference_on_its_fixture(golden, tmp_path):
