@@ -122,3 +122,48 @@ def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1, pa
     if rc != 0:
         raise RuntimeError("oracle_screen_nopattern failed: %d" % rc)
     return out[:2 * len(g)]
+
+
+def pattern_parse_ok(pattern, uam=True, uag=False):
+    """True iff the C parser accepts the pattern (the reference raises MINORgError otherwise)."""
+    n = C.c_int(0)
+    return _load().oracle_pattern_parse(pattern.encode(), C.c_int(int(uam)), C.c_int(int(uag)), C.byref(n)) == 0
+
+
+def pattern_eval(pattern, kinds, qstart, qend, qlen, uam=True, uag=False):
+    """OffTargetExpression(pattern)(alignment) by the C restatement: True / False, None on a parse error."""
+    r = _load().oracle_pattern_eval(pattern.encode(), C.c_int(int(uam)), C.c_int(int(uag)), kinds.encode(), C.c_int(qstart),
+                                    C.c_int(qend), C.c_int(qlen))
+    return None if r < 0 else bool(r)
+
+
+def screen_pattern(contigs, masks, grnas, pattern, ot_gap=0, uam=True, uag=False, threads=1, pam=None, prune=True):
+    """Exhaustive --ot-pattern screen (oracle_screen_pattern): uint32[2N] distinct-anchor counts per oriented query.
+    ot_gap is the reference attribute (gap characters allowed inside an alignment = max(1, ot_gap) - 1)."""
+    bufs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
+    offsets = np.zeros(len(bufs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bufs], out=offsets[1:])
+    blob = np.frombuffer(b"".join(bufs) or b"\0", dtype=np.uint8)
+    masks = list(masks)
+    mc = np.array([m[0] for m in masks] or [0], dtype=np.int32)
+    ms = np.array([m[1] for m in masks] or [0], dtype=np.int64)
+    me = np.array([m[2] for m in masks] or [0], dtype=np.int64)
+    g = [s.encode() if isinstance(s, str) else bytes(s) for s in grnas]
+    L = len(g[0]) if g else 1
+    gb = np.frombuffer(b"".join(g) or b"\0", dtype=np.uint8)
+    out = np.zeros(max(1, 2 * len(g)), dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if pam is None:
+        n5, len5, allow5, n3, len3, allow3, max5, max3, pamless = 0, np.zeros(1, np.int32), np.zeros(16, np.uint8), 0, \
+            np.zeros(1, np.int32), np.zeros(16, np.uint8), 0, 0, 1
+    else:
+        n5, len5, allow5 = _pam_side(pam.five_prime())
+        n3, len3, allow3 = _pam_side(pam.three_prime())
+        max5, max3, pamless = pam.five_prime_maxlen(), pam.three_prime_maxlen(), 0
+    rc = _load().oracle_screen_pattern(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me), C.c_int(len(masks)),
+                                       p(gb), C.c_int(len(g)), C.c_int(L), pattern.encode(), C.c_int(int(uam)), C.c_int(int(uag)),
+                                       C.c_int(max(1, ot_gap) - 1), C.c_int(int(prune)), C.c_int(threads), p(out), C.c_int(pamless),
+                                       C.c_int(n5), p(len5), p(allow5), C.c_int(max5), C.c_int(n3), p(len3), p(allow3), C.c_int(max3))
+    if rc != 0:
+        raise RuntimeError("oracle_screen_pattern failed: %d" % rc)
+    return out[:2 * len(g)]

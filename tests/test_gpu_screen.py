@@ -479,3 +479,49 @@ def test_piece_prefilter_odd_lengths(L, glen):
         os.environ.pop("MG_PREFILTER", None)
         q.free()
         genome.free()
+
+
+def test_pattern_counts_vs_independent_c_oracle_medium(L):
+    """--ot-pattern at medium size (270 kb x 48 gRNA x 2 strands = 2.6e7 cells per pattern): the device's per-query ANCHOR counts
+    (host-derived prefilter + DFS verifier) against oracle_screen_pattern - an independent C enumeration of E1 that parses the
+    pattern string itself, builds the reference's per-position tuples as strings (blast.py:84-120) and walks alignments from
+    the other end than nothing in the product does; it is pinned on the golden vectors executed from the reference
+    (tests/test_oracle_c.py).  Covers BASELINE configs[2]'s pattern, unaligned_as_mismatch=False / unaligned_as_gap=True and
+    PAM proximity."""
+    from minorg_b200.ot_regex import make_criteria
+    from minorg_b200.pam import PAM
+    rng = random.Random(55)
+    contigs = [("a", _random_contig(rng, 180000, "ACGT" * 12 + "N")), ("b", _random_contig(rng, 90000)), ("c", _random_contig(rng, 700))]
+    grnas = []
+    for i in range(48):
+        _, seq = contigs[i % 2]
+        p = rng.randrange(0, len(seq) - 22)
+        g = list(seq[p:p + 20].replace("N", "T"))
+        for _ in range(i % 5):
+            g[rng.randrange(20)] = rng.choice("ACGT")
+        if i % 3 == 0:
+            k = rng.randrange(2, 18)
+            g = g[:k] + g[k + 1:] + [rng.choice("ACGT")] if i % 2 else g[:k] + [rng.choice("ACGT")] + g[k:19]
+        g = "".join(g)
+        grnas.append(O.reverse_complement(g) if i % 4 == 1 else g)
+    masks = [(0, 1000, 1500), (1, 0, 300)]
+    genome = L.Genome.from_contigs(contigs)
+    genome.set_masks(masks)
+    q = L.Queries(grnas)
+    cases = [("0mg-10,1mg-11-", 2, True, False, None), ("0mg-10,1mg-11-", 0, True, False, None), ("1mg1-", 2, True, False, None),
+             ("2mg1-", 2, True, False, None), ("(0mg5,1mg6-)|(0mg6,1m7-)", 0, True, False, None), ("1m-8,2m9-", 0, True, False, None),
+             ("0m-6,3mg1-", 2, True, False, None), ("1m-8,2m9-", 0, False, False, None), ("2mg1-", 2, False, True, None),
+             ("0mg-10,1mg-11-", 2, False, False, None), ("1mg1-", 2, True, True, ".NGG"), ("1m-8,2m9-", 0, True, False, "TTTV."),
+             ("0m5|1m-6", 2, True, False, None), ("1mi-8,0d1-", 2, True, False, None)]
+    try:
+        for pat, gap, uam, uag, pam in cases:
+            crit = make_criteria(ot_pattern=pat, ot_gap=gap, ot_unaligned_as_mismatch=uam, ot_unaligned_as_gap=uag,
+                                 ot_pamless=pam is None, grna_length=20)
+            got = _resident_counts(L, genome, q, crit, PAM(pam, 20).program() if pam else None)
+            want = c_oracle.screen_pattern(contigs, masks, grnas, pat, gap, uam, uag, threads=16,
+                                           pam=O.OraclePAM(pam, 20) if pam else None).astype(np.int64)
+            assert np.array_equal(got, want), (pat, gap, uam, uag, pam, np.nonzero(got != want)[0][:10], got[got != want][:10], want[got != want][:10])
+            assert want.sum() > 0 or pam is not None, pat
+    finally:
+        q.free()
+        genome.free()

@@ -66,3 +66,76 @@ def test_c_general_oracle_matches_golden_and_python(golden):
             assert (got[:ng] + got[ng:]).tolist() == ham.tolist(), c["name"]
         n += 1
     assert n >= 17
+
+
+def _kinds(row):
+    if row["kinds"] is not None:
+        return row["kinds"]
+    return O.Alignment.from_btop(row["btop"], row["qstart"], row["qend"], row["qlen"]).kinds
+
+
+def test_c_pattern_evaluator_matches_reference_vectors(golden):
+    """oracle_pattern_eval (the C restatement of ot_regex.OffTargetExpression + blast.BlastHSP tuples, parsing the pattern
+    string itself) on every golden evaluation produced by executing the reference's own classes, parse errors included."""
+    d = golden("ot_pattern.json")
+    n = 0
+    for row in d["rows"]:
+        for key, want in row["results"].items():
+            pat, flags = key.rsplit("|", 1)
+            got = c_oracle.pattern_eval(pat, _kinds(row), row["qstart"], row["qend"], row["qlen"], flags[0] == "1", flags[1] == "1")
+            assert (got is None) if isinstance(want, str) else (got == want), (pat, flags, row)
+            n += 1
+    assert n > 10000
+    for pat, want in d["odd_patterns"].items():
+        assert c_oracle.pattern_parse_ok(pat) == (not isinstance(want, str)), pat
+
+
+def test_c_pattern_screen_matches_golden_cases_and_python(golden):
+    """oracle_screen_pattern: fail flags against the golden screens (verdicts of the reference's predicates over E1) and the
+    Python oracle; the pruned enumeration equals the unpruned one anchor for anchor."""
+    n = 0
+    for c in golden("screen_cases.json")["cases"]:
+        k = c["criteria"]
+        if k.get("pattern") is None:
+            continue
+        contigs = [tuple(x) for x in c["contigs"]]
+        names = [x[0] for x in contigs]
+        masks = [(names.index(m[1]), m[2], m[3]) for m in c["masks"]]
+        pam = None if k["pamless"] else O.OraclePAM(k["pam"], c["L"])
+        ng = len(c["grnas"])
+        got = c_oracle.screen_pattern(contigs, masks, c["grnas"], k["pattern"], k["ot_gap"], k["uam"], k["uag"], threads=2, pam=pam)
+        assert [(got[i] + got[ng + i]) > 0 for i in range(ng)] == c["fail"], c["name"]
+        slow = c_oracle.screen_pattern(contigs, masks, c["grnas"], k["pattern"], k["ot_gap"], k["uam"], k["uag"], threads=2, pam=pam,
+                                       prune=False)
+        assert got.tolist() == slow.tolist(), c["name"]
+        n += 1
+    assert n >= 12
+    rng = random.Random(17)
+    for trial, (pat, gap, uam, uag) in enumerate([("0mg-4,1mg-5-", 2, True, False), ("1mg1-", 2, True, True), ("1m3,1g4-", 2, False, False),
+                                                  ("(0mg3,1mg4-)|(0m-3,1g1-)", 2, True, False), ("0d3,1mi4-", 3, True, False),
+                                                  ("1m-4--2|0g2-5", 2, False, True)]):
+        L = 8
+        contigs = [("c%d" % i, "".join(rng.choice("ACGTacgtN") for _ in range(rng.randrange(5, 40)))) for i in range(2)]
+        grnas = []
+        for _ in range(6):
+            _, seq = rng.choice(contigs)
+            if len(seq) > L + 1 and rng.random() < 0.8:
+                p = rng.randrange(0, len(seq) - L)
+                g = list(seq[p:p + L].upper().replace("N", "A"))
+                if rng.random() < 0.5:
+                    g[rng.randrange(L)] = rng.choice("ACGT")
+                if rng.random() < 0.4:
+                    k = rng.randrange(1, L - 1)
+                    g = g[:k] + g[k + 1:] + [rng.choice("ACGT")]
+                g = "".join(g)
+                grnas.append(O.reverse_complement(g) if rng.random() < 0.5 else g)
+            else:
+                grnas.append("".join(rng.choice("ACGT") for _ in range(L)))
+        masks = [("m", "c0", 2, 2 + L)]
+        crit = O.Criteria(ot_gap=gap, pattern=pat, uam=uam, uag=uag, length=L)
+        want, _ = O.screen_exhaustive(grnas, contigs, masks, crit)
+        got = c_oracle.screen_pattern(contigs, [(0, 2, 2 + L)], grnas, pat, gap, uam, uag, threads=2)
+        ng = len(grnas)
+        assert [(got[i] + got[ng + i]) > 0 for i in range(ng)] == want, (trial, pat)
+        slow = c_oracle.screen_pattern(contigs, [(0, 2, 2 + L)], grnas, pat, gap, uam, uag, threads=2, prune=False)
+        assert got.tolist() == slow.tolist(), (trial, pat)
