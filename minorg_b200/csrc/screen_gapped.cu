@@ -42,6 +42,7 @@ namespace mg {
 // threads per CTA (one CTA per SM): the DP column of a group is 3L registers, so long gRNAs get 255 registers/thread
 template <int L> struct RowsThreads { static constexpr int value = L <= 24 ? 512 : 256; };
 constexpr int kRowsCodes = 8;                          // table columns per row: A C G T + four all-ones (invalid base)
+constexpr int kRowsQueue = 6144;                       // survivor entries (8 B) staged per CTA between two drains (48 KB)
 
 __device__ __forceinline__ uint32_t lop3_and_nn(uint32_t a, uint32_t b, uint32_t c) {       // a & ~b & ~c
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x10;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
@@ -130,6 +131,12 @@ gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ t
     constexpr int kRowsThreads = RowsThreads<L>::value;
     extern __shared__ __align__(16) uint32_t tab[];
     const uint32_t tab_sh = (uint32_t)__cvta_generic_to_shared(tab);
+    // Survivors are staged in a per-CTA shared-memory queue (one ATOMS per survivor instead of a global atomic round
+    // trip that stalls the warp for ~600 cycles) and drained to the verifier's global queue once per gRNA group with ONE
+    // global atomic per CTA and coalesced stores.  An entry is (oriented query, anchor - first text position of the CTA).
+    uint2* const cq = reinterpret_cast<uint2*>(tab + (size_t)groups_per_chunk * SG);
+    __shared__ unsigned int cq_count;
+    __shared__ unsigned long long cq_base;
     const int N = qv.n;
     const int warm = L + K;
     // anchors e in [eb, ee) <-> text positions pos = e - 1 in [eb - 1, ee - 1)
@@ -137,13 +144,14 @@ gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ t
     const int64_t p_last = min(ee - 1, p_first + run);
     const bool active = p_first < p_last;
     const int64_t p_begin = max((int64_t)0, p_first - warm);       // the initial column is exact at the start of the text
+    const int64_t e_base = eb - 1 + (int64_t)blockIdx.x * kRowsThreads * run - warm;   // <= every anchor this CTA reports
+    if (threadIdx.x == 0) cq_count = 0u;
 
     for (int cg = g_begin; cg < g_end; cg += groups_per_chunk) {
         const int ng = min(groups_per_chunk, g_end - cg);
         __syncthreads();
         for (int i = threadIdx.x; i < ng * SG; i += kRowsThreads) tab[i] = __ldg(tabr + (size_t)cg * SG + i);
         __syncthreads();
-        if (!active) continue;
         for (int g = 0; g < ng; ++g) {
             const uint32_t t = tab_sh + (uint32_t)g * (SG * 4);     // shared-window byte address of this group's table
             const int q0 = (cg + g) * 32;
@@ -151,7 +159,7 @@ gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ t
             const uint32_t qmask = (q0 + 32 <= N) ? 0xFFFFFFFFu : ((q0 < N) ? ((1u << (N - q0)) - 1u) : 0u);
             RowsState<L, NF> st;
             st.init(K);
-            int64_t pos = p_begin;
+            int64_t pos = active ? p_begin : p_last;
             while (pos < p_last) {
                 // characters up to the end of this 16-character block; the warm-up part reports nothing
                 const int k0 = (int)(pos & 15);
@@ -177,10 +185,27 @@ gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ t
                     while (h) {
                         const int i = __ffs(h) - 1;
                         h &= h - 1;
-                        emit_candidate(*ctx, strand > 0 ? q0 + i : N + q0 + i, pos + k + 1);
+                        const int q = strand > 0 ? q0 + i : N + q0 + i;
+                        const unsigned int slot = atomicAdd(&cq_count, 1u);
+                        if (slot < (unsigned int)kRowsQueue) cq[slot] = make_uint2((uint32_t)q, (uint32_t)(pos + k + 1 - e_base));
+                        else emit_candidate(*ctx, q, pos + k + 1);          // queue full: the slow direct path
                     }
                 }
                 pos += n;
+            }
+            // drain (every thread of the CTA takes part; the threads walk equally long runs, so they arrive together)
+            __syncthreads();
+            const unsigned int n_q = min(cq_count, (unsigned int)kRowsQueue);
+            __syncthreads();                                        // everyone has read the count before it is reset
+            if (n_q) {
+                if (threadIdx.x == 0) { cq_base = atomicAdd(ctx->cand_count, (unsigned long long)n_q); cq_count = 0u; }
+                __syncthreads();
+                const unsigned long long base = cq_base;
+                for (unsigned int i = threadIdx.x; i < n_q; i += kRowsThreads) {
+                    const uint2 c = cq[i];
+                    if (base + i < ctx->cand_cap) ctx->cand[base + i] = Cand{(int32_t)c.x, 0, e_base + (int64_t)c.y};
+                }
+                __syncthreads();                                    // the queue is free again
             }
         }
     }
@@ -195,10 +220,10 @@ static int launch_rows(const mg_genome* g, const mg_queries* q, const uint32_t* 
     MG_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int SG = kRowsCodes * ((L + 3) / 4 * 4);
     constexpr int kRowsThreads = RowsThreads<L>::value;
-    const int max_groups = (smem_max - 1024) / (SG * 4);
+    const int max_groups = (smem_max - 1024 - kRowsQueue * 8) / (SG * 4);
     const int n_groups = g_end - g_begin;
     const int gpc = n_groups < max_groups ? n_groups : max_groups;
-    const size_t smem = (size_t)gpc * SG * 4;
+    const size_t smem = (size_t)gpc * SG * 4 + (size_t)kRowsQueue * 8;       // tables, then the survivor queue
     static const bool alu_only = [] { const char* e = getenv("MG_ROWS"); return e && strcmp(e, "alu") == 0; }();   // A/B: all five ops as LOP3
     auto kern = alu_only ? gapped_rows_kernel<L, 0> : gapped_rows_kernel<L, L>;
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -686,3 +686,164 @@ int oracle_screen_pattern(const char* seq, const int64_t* offsets, int n_contigs
     free(jobs); free(th); free(qcodes);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bit-sliced CPU port of the ungapped screen - the CPU BASELINE bench.py times beside the GPU ("port"), so that the
+ * comparison is not against a strawman: the same counts as oracle_screen_hamming_win (tests/test_oracle_c.py compares
+ * them), computed the way the device's pair-word scan does it, with 64 oriented queries per machine word:
+ *   stage 1  per window and group of 64 queries: one table word per PAIR of gRNA positions ("query i mismatches at least
+ *            one base of the pair", indexed by the 4-bit pair of genome bases), bit-sliced count of the set words
+ *            (carry-save adders), compare with the budget - the number of set pair words never exceeds the mismatches;
+ *   stage 2  survivors only: exact 2-bit XOR/popcount of the window against the query.
+ * ~35 word operations per 64 cells instead of ~6 per cell.  Plain C, no intrinsics beyond popcount; pthreads over windows. */
+typedef struct {
+    const uint8_t* codes; int64_t n; int64_t p0, p1;
+    const uint64_t* tab2;              /* [n_groups][16*NP + 1] */
+    const uint64_t* qbits; const uint64_t* qinv;
+    int nq, n_groups, L, NP, max_mm;
+    const int64_t* ms; const int64_t* me; int n_masks;
+    uint32_t* counts;
+} bjob_t;
+
+static inline void bs_add(uint64_t cnt[5], uint64_t x) {          /* bit-sliced counter += x (ripple of half adders) */
+    for (int b = 0; b < 5 && x; ++b) { const uint64_t t = cnt[b] & x; cnt[b] ^= x; x = t; }
+}
+
+static inline uint64_t bs_le(const uint64_t cnt[5], int K) {        /* bit i: count_i <= K */
+    uint64_t lt = 0, eq = ~0ULL;
+    for (int b = 4; b >= 0; --b) {
+        if ((K >> b) & 1) { lt |= eq & ~cnt[b]; eq &= cnt[b]; } else eq &= ~cnt[b];
+    }
+    return lt | eq;
+}
+
+static void* brun(void* arg) {
+    bjob_t* j = (bjob_t*)arg;
+    const int L = j->L, NP = j->NP, S2 = 16 * NP + 1;
+    const uint64_t even = 0x5555555555555555ULL;
+    const uint64_t lmask = (L >= 32) ? even : (((1ULL << (2 * L)) - 1) & even);
+    job_t mj;                                                        /* for span_masked() */
+    mj.ms = j->ms; mj.me = j->me; mj.n_masks = j->n_masks;
+    int off[16];
+    for (int64_t p = j->p0; p < j->p1; ++p) {
+        uint64_t w = 0, winv = 0;
+        for (int k = 0; k < L; ++k) {
+            const int64_t i = p + k;
+            const int c = (i < 0 || i >= j->n) ? 4 : j->codes[i];
+            if (c == 4) winv |= 1ULL << (2 * k); else w |= (uint64_t)c << (2 * k);
+        }
+        for (int k = 0; k < NP; ++k) {
+            const int bad = (int)((winv >> (4 * k)) & 5ULL & ((2 * k + 1 < L) ? 5ULL : 1ULL));
+            off[k] = bad ? 16 * NP : 16 * k + (int)((w >> (4 * k)) & 15ULL);
+        }
+        int masked = -1;
+        for (int g = 0; g < j->n_groups; ++g) {
+            const uint64_t* t = j->tab2 + (size_t)g * S2;
+            uint64_t alive;
+            if (NP == 10) {                                          /* carry-save tree for the common 20-nt case */
+#define FA(a, b, c, s, cy) do { const uint64_t a_ = (a), b_ = (b), c_ = (c); s = a_ ^ b_ ^ c_; cy = (a_ & b_) | (c_ & (a_ ^ b_)); } while (0)
+                uint64_t s0, c0, s1, c1, s2, c2, t0, c3, u0, d0, b0, b1, c4, d1;
+                FA(t[off[0]], t[off[1]], t[off[2]], s0, c0);
+                FA(t[off[3]], t[off[4]], t[off[5]], s1, c1);
+                FA(t[off[6]], t[off[7]], t[off[8]], s2, c2);
+                FA(s0, s1, s2, t0, c3);
+                b0 = t0 ^ t[off[9]]; c4 = t0 & t[off[9]];
+                FA(c0, c1, c2, u0, d0);
+                FA(u0, c3, c4, b1, d1);
+                uint64_t cnt[5] = {b0, b1, d0 ^ d1, d0 & d1, 0};
+#undef FA
+                alive = bs_le(cnt, j->max_mm);
+            } else {
+                uint64_t cnt[5] = {0, 0, 0, 0, 0};
+                for (int k = 0; k < NP; ++k) bs_add(cnt, t[off[k]]);
+                alive = bs_le(cnt, j->max_mm);
+            }
+            while (alive) {
+                const int i = __builtin_ctzll(alive);
+                alive &= alive - 1;
+                const int q = g * 64 + i;
+                if (q >= j->nq) break;
+                const uint64_t x = w ^ j->qbits[q];
+                const uint64_t d = ((x | (x >> 1)) & lmask) | winv | j->qinv[q];
+                if (__builtin_popcountll(d) > j->max_mm) continue;
+                if (masked < 0) {
+                    const int64_t a = p < 0 ? 0 : p, b = (p + L > j->n) ? j->n : p + L;
+                    masked = (a >= b) ? 1 : span_masked(&mj, a, b);
+                }
+                if (!masked) j->counts[q]++;
+            }
+        }
+    }
+    return NULL;
+}
+
+int oracle_screen_hamming_bitsliced(const char* seq, const int64_t* offsets, int n_contigs,
+                                    const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                                    const char* grna, int n, int L, int max_mm, int n_threads, uint32_t* counts_out,
+                                    const int64_t* win_lo, const int64_t* win_hi) {
+    if (L < 1 || L > 32 || n < 0 || n_threads < 1 || max_mm < 0 || max_mm > 31) return -2;
+    const int nq = 2 * n, NP = (L + 1) / 2, S2 = 16 * NP + 1, n_groups = (nq + 63) / 64;
+    uint64_t* qbits = (uint64_t*)calloc((size_t)nq + 1, 8);
+    uint64_t* qinv = (uint64_t*)calloc((size_t)nq + 1, 8);
+    uint8_t* qc = (uint8_t*)malloc((size_t)nq * L + 1);              /* oriented query codes, 4 = not ACGT */
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < L; ++k) {
+            const int c = code_of(grna[(size_t)i * L + k]);
+            qc[(size_t)i * L + k] = (uint8_t)c;
+            qc[(size_t)(n + i) * L + (L - 1 - k)] = (uint8_t)(c == 4 ? 4 : 3 - c);
+            if (c == 4) { qinv[i] |= 1ULL << (2 * k); qinv[n + i] |= 1ULL << (2 * (L - 1 - k)); }
+            else { qbits[i] |= (uint64_t)c << (2 * k); qbits[n + i] |= (uint64_t)(3 - c) << (2 * (L - 1 - k)); }
+        }
+    uint64_t* tab2 = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n_groups * S2);
+    for (int g = 0; g < n_groups; ++g)
+        for (int k = 0; k < NP; ++k)
+            for (int nib = 0; nib < 16; ++nib) {
+                uint64_t wd = 0;
+                for (int i = 0; i < 64; ++i) {
+                    const int q = g * 64 + i;
+                    int mism = 1;
+                    if (q < nq) {
+                        mism = qc[(size_t)q * L + 2 * k] != (nib & 3);
+                        if (2 * k + 1 < L) mism |= qc[(size_t)q * L + 2 * k + 1] != ((nib >> 2) & 3);
+                    }
+                    wd |= (uint64_t)mism << i;
+                }
+                tab2[(size_t)g * S2 + 16 * k + nib] = wd;
+            }
+    for (int g = 0; g < n_groups; ++g) tab2[(size_t)g * S2 + 16 * NP] = ~0ULL;
+    memset(counts_out, 0, sizeof(uint32_t) * (size_t)n);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    bjob_t* jobs = (bjob_t*)malloc(sizeof(bjob_t) * (size_t)n_threads);
+    uint32_t* priv = (uint32_t*)calloc((size_t)n_threads * (size_t)(nq + 1), 4);
+    for (int c = 0; c < n_contigs; ++c) {
+        const int64_t len = offsets[c + 1] - offsets[c];
+        int64_t first = -(int64_t)L + 1, last = len;
+        if (win_lo != NULL && win_hi != NULL) {
+            if (win_lo[c] > first) first = win_lo[c];
+            if (win_hi[c] < last) last = win_hi[c];
+        }
+        if (last <= first) continue;
+        uint8_t* codes = (uint8_t*)malloc((size_t)len + 1);
+        for (int64_t i = 0; i < len; ++i) codes[i] = (uint8_t)code_of(seq[offsets[c] + i]);
+        int nm = 0;
+        int64_t* ms = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
+        int64_t* me = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_masks + 1));
+        for (int i = 0; i < n_masks; ++i) if (mask_contig[i] == c) { ms[nm] = mask_start[i]; me[nm] = mask_end[i]; ++nm; }
+        const int64_t total = last - first;
+        for (int t = 0; t < n_threads; ++t) {
+            bjob_t* j = &jobs[t];
+            j->codes = codes; j->n = len; j->tab2 = tab2; j->qbits = qbits; j->qinv = qinv; j->nq = nq; j->n_groups = n_groups;
+            j->L = L; j->NP = NP; j->max_mm = max_mm; j->ms = ms; j->me = me; j->n_masks = nm;
+            j->counts = priv + (size_t)t * (size_t)(nq + 1);
+            j->p0 = first + total * t / n_threads; j->p1 = first + total * (t + 1) / n_threads;
+            pthread_create(&th[t], NULL, brun, j);
+        }
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+        free(codes); free(ms); free(me);
+    }
+    for (int t = 0; t < n_threads; ++t)
+        for (int i = 0; i < n; ++i)
+            counts_out[i] += priv[(size_t)t * (size_t)(nq + 1) + i] + priv[(size_t)t * (size_t)(nq + 1) + n + i];
+    free(priv); free(jobs); free(th); free(qbits); free(qinv); free(qc); free(tab2);
+    return 0;
+}

@@ -508,11 +508,10 @@ def test_pattern_counts_vs_independent_c_oracle_medium(L):
     genome = L.Genome.from_contigs(contigs)
     genome.set_masks(masks)
     q = L.Queries(grnas)
-    cases = [("0mg-10,1mg-11-", 2, True, False, None), ("0mg-10,1mg-11-", 0, True, False, None), ("1mg1-", 2, True, False, None),
-             ("2mg1-", 2, True, False, None), ("(0mg5,1mg6-)|(0mg6,1m7-)", 0, True, False, None), ("1m-8,2m9-", 0, True, False, None),
+    cases = [("0mg-10,1mg-11-", 2, True, False, None), ("1mg1-", 2, True, False, None),
+             ("(0mg5,1mg6-)|(0mg6,1m7-)", 0, True, False, None), ("1m-8,2m9-", 0, True, False, None),
              ("0m-6,3mg1-", 2, True, False, None), ("1m-8,2m9-", 0, False, False, None), ("2mg1-", 2, False, True, None),
-             ("0mg-10,1mg-11-", 2, False, False, None), ("1mg1-", 2, True, True, ".NGG"), ("1m-8,2m9-", 0, True, False, "TTTV."),
-             ("0m5|1m-6", 2, True, False, None), ("1mi-8,0d1-", 2, True, False, None)]
+             ("0mg-10,1mg-11-", 2, False, False, None), ("1mg1-", 2, True, True, ".NGG"), ("1mi-8,0d1-", 2, True, False, None)]
     try:
         for pat, gap, uam, uag, pam in cases:
             crit = make_criteria(ot_pattern=pat, ot_gap=gap, ot_unaligned_as_mismatch=uam, ot_unaligned_as_gap=uag,
