@@ -190,7 +190,8 @@ typedef struct {
  * MINORg.py:2123-2144).  d_counts: DEVICE array of 2*N uint32 that is ADDED to (query i / N+i = plus /
  * minus orientation of gRNA i): the number of problematic, unmasked alignments anchored in this genome.
  * gRNA i fails the background check iff d_counts[i] + d_counts[N+i] > 0.  No early exit: every cell is
- * evaluated.  window range [win_begin, win_end) in global coordinates selects a shard (pass 0, -1 for all).
+ * evaluated, and the counts are exact in every mode: each problematic anchor (strand, virtual alignment end) is counted once,
+ * whatever prefilter found it and however the window range is cut into shards or slices.  window range [win_begin, win_end) in global coordinates selects a shard (pass 0, -1 for all).
  * pam may be NULL when crit->pamless. */
 int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
               int64_t win_begin, int64_t win_end, uint32_t* d_counts, void* stream);
@@ -204,7 +205,9 @@ int mg_screen_to_host(const mg_genome* g, const mg_queries* q, const mg_criteria
  * ASCII genome + ASCII gRNAs in host memory -> H2D, pack, screen, D2H.  counts_out: N uint32 (both
  * orientations summed).  The subject is processed in batches of whole contigs; the next batch is copied and
  * packed on an internal stream while the current one is screened on `stream` (pinned `seq` makes that copy
- * asynchronous).  Returns after everything, including the D2H of the counts, has completed. */
+ * asynchronous).  Returns after everything, including the D2H of the counts, has completed.  The query tables of the
+ * previous call on this thread are kept and reused when the gRNA bytes are the same (a pipeline screens one gRNA set against
+ * subject after subject, MINORg.py:2198-2207), as are the internal copy stream and the pooled device scratch. */
 int mg_screen_host(const char* seq, const int64_t* offsets, int n_contigs,
                    const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
                    const char* grna, int n, int len, const mg_criteria* crit, const mg_pam* pam,

@@ -216,6 +216,7 @@ class MINORg:
         """Generate all possible gRNA from self.target based on self.pam and self.length."""
         if not self.target:
             raise MINORgError("MINORg.grna requires self.target (FASTA of target sequences)")
+        self._check_limits([self.length])
         self.grna_hits = self._generate_grna(self.target, pam=self.pam, length=self.length)
         self.write_all_grna_fasta()
         if self.auto_update_files:
@@ -310,7 +311,19 @@ class MINORg:
                 for m in masked:
                     f.write("\t".join([str(inv[fname]), m.molecule, str(m.start), str(m.end), m.masked]) + "\n")
 
+    def _check_limits(self, lengths):
+        """The device kernels hold a gRNA in one 64-bit 2-bit word and the gap search in MG_MAX_GAPS diagonals; the
+        reference has no such limits (generate_grna.py:23), so exceeding them must fail HERE, by name, not deep in C."""
+        too_long = sorted({n for n in lengths if n > _lib.MG_MAX_GRNA_LEN or n < 1})
+        if too_long:
+            raise MINORgError("gRNA length(s) %s outside 1..%d: not supported by the device screen (MG_MAX_GRNA_LEN)"
+                              % (too_long, _lib.MG_MAX_GRNA_LEN))
+        if max(1, int(self.ot_gap)) - 1 > _lib.MG_MAX_GAPS:
+            raise MINORgError("ot_gap=%s allows more than %d gap characters: not supported by the device screen (MG_MAX_GAPS)"
+                              % (self.ot_gap, _lib.MG_MAX_GAPS))
+
     def _criteria(self, length):
+        self._check_limits([length])
         return make_criteria(ot_mismatch=self.ot_mismatch, ot_gap=self.ot_gap, ot_pattern=self.ot_pattern,
                              ot_unaligned_as_mismatch=self.ot_unaligned_as_mismatch,
                              ot_unaligned_as_gap=self.ot_unaligned_as_gap, ot_pamless=self.ot_pamless,
@@ -374,6 +387,7 @@ class MINORg:
             raise MINORgError("MINORg.filter_background requires gRNA (generated with self.grna())")
         if self.grna_fasta is None:
             self.write_all_grna_fasta()
+        self._check_limits({len(s) for s in fasta_to_dict(self.grna_fasta).values()})     # before any device work
         ref, query, bg = self._subject_groups()
         files = []
         for enabled, group in (((self.screen_reference or self.query_reference) and ref, ref), (query, query), (bg, bg)):

@@ -168,3 +168,23 @@ def test_cli_full_then_resume_from_map(cfg1, tmp_path):
     fail3, _ = _oracle_background(cfg1, want, ["subset_ref_TAIR10.fasta", "subset_9654.fasta", "subset_9655.fasta"], 3)
     assert {r[1]: r[-3] for r in rows2[1:]} == {s: ("fail" if fl else "pass") for (s, _), fl in zip(want, fail3)}
     assert main(["minimumset", "-m", str(all_map), "-d", str(out), "--prefix", "run", "-s", "1"]) == 0
+
+
+def test_class_rejects_device_limits_by_name(tmp_path):
+    """gRNA longer than MG_MAX_GRNA_LEN and ot_gap beyond MG_MAX_GAPS fail in the MINORg-shaped class with a MINORgError
+    that names the limit - before any device call (the reference itself has no such limits, generate_grna.py:23)."""
+    import pytest
+    from minorg_b200.MINORg import MINORg, MINORgError
+    t = tmp_path / "t.fasta"
+    t.write_text(">t1\n" + "ACGTTGCAAGGCTTAGCGG" * 12 + "\n")
+    m = MINORg(directory=str(tmp_path / "out"), prefix="x")
+    m.target = str(t)
+    m.length = 33
+    with pytest.raises(MINORgError, match="MG_MAX_GRNA_LEN"):
+        m.grna()
+    m.length = 20
+    m.ot_gap = 6
+    with pytest.raises(MINORgError, match="MG_MAX_GAPS"):
+        m._criteria(20)
+    m.ot_gap = 4
+    m._criteria(20)

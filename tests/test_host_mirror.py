@@ -454,3 +454,4 @@ def test_map_reader_matches_reference_on_its_fixture(golden, tmp_path):
         assert out.read_text() == row["rewritten"], row["name"]
         n += 1
     assert n == 4
+

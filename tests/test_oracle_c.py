@@ -139,3 +139,31 @@ def test_c_pattern_screen_matches_golden_cases_and_python(golden):
         assert [(got[i] + got[ng + i]) > 0 for i in range(ng)] == want, (trial, pat)
         slow = c_oracle.screen_pattern(contigs, [(0, 2, 2 + L)], grnas, pat, gap, uam, uag, threads=2, prune=False)
         assert got.tolist() == slow.tolist(), (trial, pat)
+
+
+def test_bitsliced_cpu_port_equals_the_scalar_oracle():
+    """oracle_screen_hamming_bitsliced (the CPU baseline bench.py times) returns the counts of oracle_screen_hamming_win on
+    ragged inputs: N runs, lower case, short contigs, masks, window ranges, odd lengths, every budget class."""
+    import numpy as np
+    rng = random.Random(31)
+    for L, M in ((20, 4), (20, 0), (23, 3), (8, 1), (32, 5), (1, 0), (21, 6), (20, 7)):
+        contigs = [("a", "".join(rng.choice("ACGTacgtN" + "ACGT" * 6) for _ in range(9000))), ("b", "".join(rng.choice("ACGT") for _ in range(700))),
+                   ("c", "ACG"), ("d", "")]
+        grnas = []
+        for i in range(150):
+            if i % 2:
+                p = rng.randrange(0, 9000 - L)
+                s = list(contigs[0][1][p:p + L].upper().replace("N", "A"))
+                for _ in range(rng.randrange(0, M + 2)):
+                    s[rng.randrange(L)] = rng.choice("ACGT")
+                grnas.append("".join(s))
+            else:
+                grnas.append("".join(rng.choice("ACGTN" + "ACGT" * 5) for _ in range(L)))
+        blob = np.frombuffer("".join(s for _, s in contigs).encode(), dtype=np.uint8)
+        off = np.array([0, 9000, 9700, 9703, 9703], dtype=np.int64)
+        masks = [(0, 100, 400), (1, 0, 50)]
+        for ranges in (None, [(-5, 4000), (10, 600), (0, 1), (0, 0)]):
+            a = c_oracle.screen_hamming_arrays(blob, off, masks, grnas, M, 3, ranges)
+            b = c_oracle.screen_hamming_arrays(blob, off, masks, grnas, M, 3, ranges, bitsliced=True)
+            assert a.tolist() == b.tolist(), (L, M, ranges)
+        assert a.sum() > 0
