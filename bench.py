@@ -364,6 +364,9 @@ def main():
             want_baseline = world == 1 and not args.no_cpu_baseline
             parity, cpu_baseline = parity_check(torch, _lib, genome, queries, crit, grnas, masks, ascii_dev, clens,
                                                 3.0, args.cpu_seconds if want_baseline else 0.0, threads, stream, device)
+        if rank == 0 and args.gapped:
+            parity = general_parity(torch, _lib, genome, queries, crit, grnas, masks, ascii_dev, clens, threads, stream, device,
+                                    span=20000, n_sub=min(n, 256), ot_gap=2, max_mismatch=MAX_MISMATCH)
         shard_check = window_shard_check(torch, dist, _lib, rank, world, device, stream, queries, crit, grnas, clens,
                                          targets_all, ascii_dev if 0 in my_genomes else None, masks if 0 in my_genomes else None)
 
@@ -387,9 +390,16 @@ def main():
             m1.record()
             torch.cuda.synchronize()
             sec = m0.elapsed_time(m1) / 1e3
-            other_modes.append({"mode": label, "n_grna": n_sub, "seconds": sec, "value": n_sub * total_bases / 1e9 / sec,
-                                "unit": "gRNA*Gbp/s", "tcell_per_s": 2.0 * n_sub * total_bases / sec / 1e12,
-                                "grna_failed": int(((c_sub[:n_sub] + c_sub[n_sub:]) > 0).sum().item())})
+            entry = {"mode": label, "n_grna": n_sub, "seconds": sec, "value": n_sub * total_bases / 1e9 / sec,
+                     "unit": "gRNA*Gbp/s", "tcell_per_s": 2.0 * n_sub * total_bases / sec / 1e12,
+                     "grna_failed": int(((c_sub[:n_sub] + c_sub[n_sub:]) > 0).sum().item())}
+            if not args.no_checks and ("ot_gap" in kw or "ot_pattern" in kw):
+                # the same criterion on a slice of the full-size genome against the exhaustive C oracle (anchor counts)
+                entry["parity_check"] = general_parity(torch, _lib, genome, q_sub, crit_m, grnas[:n_sub], masks, ascii_dev, clens, threads,
+                                                       stream, device, span=20000 if "ot_pattern" not in kw else 200000,
+                                                       n_sub=min(n_sub, 256), ot_gap=kw.get("ot_gap", 0),
+                                                       max_mismatch=max(1, kw.get("ot_mismatch", 1)) - 1, pattern=kw.get("ot_pattern"))
+            other_modes.append(entry)
             if q_sub is not queries:
                 q_sub.free()
 
@@ -522,6 +532,44 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def general_parity(torch, _lib, genome, q, crit, grnas, masks, ascii_dev, clens, threads, stream, device, span, n_sub, ot_gap=0,
+                   max_mismatch=None, pattern=None):
+    """Gapped / pattern criteria on the FULL-SIZE resident genome against the exhaustive C oracles (oracle_screen_nopattern_win
+    / oracle_screen_pattern) on the windows that start within `span` bases of the contig 0 / contig 1 boundary of genome 0, for the
+    first n_sub gRNA: per-oriented-query anchor counts, one to one."""
+    from oracle import c_oracle
+    c_oracle.build()
+    len0, len1 = clens[0], clens[1]
+    span = int(min(span, len0, len1))
+    n = len(grnas)
+    host = ascii_dev[:len0 + len1].cpu().numpy()
+    contigs = [("c0", host[:len0].tobytes()), ("c1", host[len0:len0 + len1].tobytes())]
+    m01 = [(c, s, e) for c, s, e in masks if c < 2]
+    ranges = [(len0 - span, len0), (-GRNA_LEN, span)]
+    t0 = time.perf_counter()
+    if pattern is None:
+        want = c_oracle.screen_nopattern(contigs, m01, grnas[:n_sub], max_mismatch, max(1, ot_gap) - 1, threads=threads, win_ranges=ranges)
+    else:
+        want = c_oracle.screen_pattern(contigs, m01, grnas[:n_sub], pattern, ot_gap, threads=threads, win_ranges=ranges)
+    cpu_s = time.perf_counter() - t0
+    want = want.astype(np.int64)
+    c = torch.zeros(2 * n, dtype=torch.int32, device=device)
+    _lib.screen(genome, q, crit, None, c.data_ptr(), win_begin=genome.contig_global_start(0) + len0 - span,
+                win_end=genome.contig_global_start(1) + span, stream=stream)
+    torch.cuda.synchronize()
+    got = c.cpu().numpy().astype(np.int64)
+    got = np.concatenate([got[:n_sub], got[n:n + n_sub]])
+    equal = bool(np.array_equal(got, want))
+    out = {"window_bp": 2 * span + GRNA_LEN - 1, "n_grna": n_sub, "equal": equal, "anchors_total": int(want.sum()),
+           "queries_with_hits": int((want > 0).sum()),
+           "oracle": "oracle/screen_oracle.c %s, %d threads, %.1f s" % ("oracle_screen_pattern" if pattern else "oracle_screen_nopattern_win", threads, cpu_s)}
+    if not equal:
+        bad = np.nonzero(got != want)[0]
+        out["first_differences"] = [(int(i), int(got[i]), int(want[i])) for i in bad[:5]]
+    assert equal, "parity: device anchor counts differ from the C oracle: %s" % out
+    return out
 
 
 def parity_check(torch, _lib, genome, queries, crit, grnas, masks, ascii_dev, clens, seconds, baseline_seconds, threads, stream, device):

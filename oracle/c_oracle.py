@@ -93,7 +93,16 @@ def _pam_side(side_regex):
     return (len(alts) if side_regex else 0), lens, allow
 
 
-def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1, pam=None):
+def _win_arrays(win_ranges, n_contigs):
+    if win_ranges is None:
+        return None, None
+    lo = np.array([r[0] for r in win_ranges], dtype=np.int64)
+    hi = np.array([r[1] for r in win_ranges], dtype=np.int64)
+    assert len(lo) == n_contigs
+    return lo, hi
+
+
+def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1, pam=None, win_ranges=None):
     """Exhaustive no-pattern screen with gaps/trimming: uint32[2N] distinct-anchor counts per oriented query
     ([i] = '+' strand, [N+i] = '-' strand) - see oracle_screen_nopattern in screen_oracle.c.  pam = an
     oracle.minorg_oracle.OraclePAM to require PAM proximity (ot_pamless=False), None for the PAM-less default."""
@@ -117,10 +126,12 @@ def screen_nopattern(contigs, masks, grnas, max_mismatch, max_gap, threads=1, pa
         n5, len5, allow5 = _pam_side(pam.five_prime())
         n3, len3, allow3 = _pam_side(pam.three_prime())
         max5, max3, pamless = pam.five_prime_maxlen(), pam.three_prime_maxlen(), 0
-    rc = _load().oracle_screen_nopattern_pam(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
+    lo, hi = _win_arrays(win_ranges, len(offsets) - 1)
+    rc = _load().oracle_screen_nopattern_win(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me),
                                              C.c_int(len(masks)), p(gb), C.c_int(len(g)), C.c_int(L), C.c_int(max_mismatch),
                                              C.c_int(max_gap), C.c_int(threads), p(out), C.c_int(pamless),
-                                             C.c_int(n5), p(len5), p(allow5), C.c_int(max5), C.c_int(n3), p(len3), p(allow3), C.c_int(max3))
+                                             C.c_int(n5), p(len5), p(allow5), C.c_int(max5), C.c_int(n3), p(len3), p(allow3), C.c_int(max3),
+                                             None if lo is None else p(lo), None if hi is None else p(hi))
     if rc != 0:
         raise RuntimeError("oracle_screen_nopattern failed: %d" % rc)
     return out[:2 * len(g)]
@@ -139,7 +150,7 @@ def pattern_eval(pattern, kinds, qstart, qend, qlen, uam=True, uag=False):
     return None if r < 0 else bool(r)
 
 
-def screen_pattern(contigs, masks, grnas, pattern, ot_gap=0, uam=True, uag=False, threads=1, pam=None, prune=True):
+def screen_pattern(contigs, masks, grnas, pattern, ot_gap=0, uam=True, uag=False, threads=1, pam=None, prune=True, win_ranges=None):
     """Exhaustive --ot-pattern screen (oracle_screen_pattern): uint32[2N] distinct-anchor counts per oriented query.
     ot_gap is the reference attribute (gap characters allowed inside an alignment = max(1, ot_gap) - 1)."""
     bufs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
@@ -162,10 +173,12 @@ def screen_pattern(contigs, masks, grnas, pattern, ot_gap=0, uam=True, uag=False
         n5, len5, allow5 = _pam_side(pam.five_prime())
         n3, len3, allow3 = _pam_side(pam.three_prime())
         max5, max3, pamless = pam.five_prime_maxlen(), pam.three_prime_maxlen(), 0
+    lo, hi = _win_arrays(win_ranges, len(offsets) - 1)
     rc = _load().oracle_screen_pattern(p(blob), p(offsets), C.c_int(len(offsets) - 1), p(mc), p(ms), p(me), C.c_int(len(masks)),
                                        p(gb), C.c_int(len(g)), C.c_int(L), pattern.encode(), C.c_int(int(uam)), C.c_int(int(uag)),
                                        C.c_int(max(1, ot_gap) - 1), C.c_int(int(prune)), C.c_int(threads), p(out), C.c_int(pamless),
-                                       C.c_int(n5), p(len5), p(allow5), C.c_int(max5), C.c_int(n3), p(len3), p(allow3), C.c_int(max3))
+                                       C.c_int(n5), p(len5), p(allow5), C.c_int(max5), C.c_int(n3), p(len3), p(allow3), C.c_int(max3),
+                                       None if lo is None else p(lo), None if hi is None else p(hi))
     if rc != 0:
         raise RuntimeError("oracle_screen_pattern failed: %d" % rc)
     return out[:2 * len(g)]

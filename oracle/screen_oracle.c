@@ -221,7 +221,17 @@ typedef struct {
     int q0, q1; uint32_t* counts; /* [2*nq] shared, disjoint slots per thread */
     int pamless, n5, n3, max5, max3;
     const int32_t* len5; const uint8_t* allow5; const int32_t* len3; const uint8_t* allow3;
+    int64_t wlo, whi;              /* only anchors owned by the windows that START in [wlo, whi) (forward contig coordinates) count */
 } gjob_t;
+
+/* Anchor range [*e0, *e1) (strand coordinates) owned by the forward windows [wlo, whi): a window [p, p+L) owns the '+' anchor
+ * p + L and the '-' anchor n - p (its end in reverse-complement coordinates) - mg_screen's ownership rule for shards. */
+static void anchor_range(int strand, int64_t n, int L, int64_t wlo, int64_t whi, int64_t* e0, int64_t* e1) {
+    if (strand > 0) { *e0 = wlo + L; *e1 = whi + L; }
+    else { *e0 = n - whi + 1; *e1 = n - wlo + 1; }
+    if (*e0 < 0) *e0 = 0;
+    if (*e1 > n + L + 1) *e1 = n + L + 1;
+}
 
 static void* g_run(void* arg) {
     gjob_t* j = (gjob_t*)arg;
@@ -236,10 +246,15 @@ static void* g_run(void* arg) {
             c.ms = j->ms; c.me = j->me; c.n_masks = j->n_masks; c.strand = strand; c.ends = ends;
             c.pamless = j->pamless; c.n5 = j->n5; c.n3 = j->n3; c.max5 = j->max5; c.max3 = j->max3;
             c.len5 = j->len5; c.allow5 = j->allow5; c.len3 = j->len3; c.allow3 = j->allow3;
-            for (int64_t s = 0; s < j->n; ++s)
+            int64_t e0, e1;
+            anchor_range(strand, j->n, j->L, j->wlo, j->whi, &e0, &e1);
+            if (e1 <= e0) continue;
+            /* an alignment that ends (virtually) at e starts no earlier than e - L - Gp */
+            const int64_t s_lo = e0 - j->L - j->Gp - 1 < 0 ? 0 : e0 - j->L - j->Gp - 1, s_hi = e1 < j->n ? e1 : j->n;
+            for (int64_t s = s_lo; s < s_hi; ++s)
                 for (int qs = 0; qs < j->L && qs <= c.B; ++qs) { c.qs = qs; c.s = s; g_dfs(&c, qs, s, 0, 0, 0); }
             uint32_t cnt = 0;
-            for (size_t b = 0; b < nbytes; ++b) cnt += (uint32_t)__builtin_popcount(ends[b]);
+            for (int64_t e = e0; e < e1; ++e) cnt += (ends[e >> 3] >> (e & 7)) & 1u;
             j->counts[strand > 0 ? qi : j->nq + qi] += cnt;
         }
     }
@@ -263,11 +278,30 @@ int oracle_screen_nopattern(const char* seq, const int64_t* offsets, int n_conti
 
 /* Same with the PAM proximity requirement: a PAM side = n alternatives of fixed length, position k of alternative a
  * allows the bases whose bit is set in allow[a*16 + k] (bit 0..3 = A,C,G,T); max5/max3 = PAM.five/three_prime_maxlen(). */
+int oracle_screen_nopattern_win(const char* seq, const int64_t* offsets, int n_contigs,
+                                const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                                const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out,
+                                int pamless, int n5, const int32_t* len5, const uint8_t* allow5, int max5,
+                                int n3, const int32_t* len3, const uint8_t* allow3, int max3,
+                                const int64_t* win_lo, const int64_t* win_hi);
+
 int oracle_screen_nopattern_pam(const char* seq, const int64_t* offsets, int n_contigs,
                                 const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
                                 const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out,
                                 int pamless, int n5, const int32_t* len5, const uint8_t* allow5, int max5,
                                 int n3, const int32_t* len3, const uint8_t* allow3, int max3) {
+    return oracle_screen_nopattern_win(seq, offsets, n_contigs, mask_contig, mask_start, mask_end, n_masks, grna, n, L, max_mm, max_gap,
+                                       n_threads, counts_out, pamless, n5, len5, allow5, max5, n3, len3, allow3, max3, NULL, NULL);
+}
+
+/* win_lo / win_hi (NULL = everything): per contig, only the anchors owned by the windows that start in [win_lo[c], win_hi[c])
+ * are counted - the C side of mg_screen(win_begin, win_end) for the gapped criteria (bench.py --gapped parity slice). */
+int oracle_screen_nopattern_win(const char* seq, const int64_t* offsets, int n_contigs,
+                                const int32_t* mask_contig, const int64_t* mask_start, const int64_t* mask_end, int n_masks,
+                                const char* grna, int n, int L, int max_mm, int max_gap, int n_threads, uint32_t* counts_out,
+                                int pamless, int n5, const int32_t* len5, const uint8_t* allow5, int max5,
+                                int n3, const int32_t* len3, const uint8_t* allow3, int max3,
+                                const int64_t* win_lo, const int64_t* win_hi) {
     if (L < 1 || L > 32 || n < 0 || n_threads < 1 || max_gap < 0 || max_gap > 3) return -2;
     uint8_t* qcodes = (uint8_t*)malloc((size_t)n * L + 1);
     for (size_t i = 0; i < (size_t)n * L; ++i) qcodes[i] = (uint8_t)code_of(grna[i]);
@@ -293,6 +327,7 @@ int oracle_screen_nopattern_pam(const char* seq, const int64_t* offsets, int n_c
             j->counts = counts_out;
             j->pamless = pamless; j->n5 = n5; j->n3 = n3; j->max5 = max5; j->max3 = max3;
             j->len5 = len5; j->allow5 = allow5; j->len3 = len3; j->allow3 = allow3;
+            j->wlo = win_lo ? win_lo[c] : -(int64_t)L - 8; j->whi = win_hi ? win_hi[c] : len + 8;
             pthread_create(&th[t], NULL, g_run, j);
         }
         for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
@@ -581,6 +616,7 @@ typedef struct {
     int q0, q1; uint32_t* counts;
     int pamless, n5, n3, max5, max3;
     const int32_t* len5; const uint8_t* allow5; const int32_t* len3; const uint8_t* allow3;
+    int64_t wlo, whi;              /* forward window starts whose anchors count (see anchor_range) */
 } pjob_t;
 
 static void* p_run(void* arg) {
@@ -598,13 +634,20 @@ static void* p_run(void* arg) {
             c.g.ms = j->ms; c.g.me = j->me; c.g.n_masks = j->n_masks; c.g.strand = strand; c.g.ends = ends;
             c.g.pamless = j->pamless; c.g.n5 = j->n5; c.g.n3 = j->n3; c.g.max5 = j->max5; c.g.max3 = j->max3;
             c.g.len5 = j->len5; c.g.allow5 = j->allow5; c.g.len3 = j->len3; c.g.allow3 = j->allow3;
+            int64_t e0, e1;
+            anchor_range(strand, j->n, j->L, j->wlo, j->whi, &e0, &e1);
+            if (e1 <= e0) continue;
             for (int qe = j->L; qe >= 1; --qe) {
                 c.qe = qe;
                 if (c.prune && !p_may_succeed(&c, 0, qe)) continue;     /* the 3' tail alone already decides */
-                for (int64_t t = 1; t <= j->n; ++t) { c.t_end = t; p_dfs(&c, qe, t, 0, 0, 0, 0); }
+                /* anchor e = t + (L - qe) must lie in [e0, e1) */
+                int64_t t0 = e0 - (j->L - qe), t1 = e1 - (j->L - qe);
+                if (t0 < 1) t0 = 1;
+                if (t1 > j->n + 1) t1 = j->n + 1;
+                for (int64_t t = t0; t < t1; ++t) { c.t_end = t; p_dfs(&c, qe, t, 0, 0, 0, 0); }
             }
             uint32_t cnt = 0;
-            for (size_t b = 0; b < nbytes; ++b) cnt += (uint32_t)__builtin_popcount(ends[b]);
+            for (int64_t e = e0; e < e1; ++e) cnt += (ends[e >> 3] >> (e & 7)) & 1u;
             j->counts[strand > 0 ? qi : j->nq + qi] += cnt;
         }
     }
@@ -646,7 +689,8 @@ int oracle_screen_pattern(const char* seq, const int64_t* offsets, int n_contigs
                           const char* grna, int n, int L, const char* pattern, int uam, int uag, int gcap, int prune,
                           int n_threads, uint32_t* counts_out,
                           int pamless, int n5, const int32_t* len5, const uint8_t* allow5, int max5,
-                          int n3, const int32_t* len3, const uint8_t* allow3, int max3) {
+                          int n3, const int32_t* len3, const uint8_t* allow3, int max3,
+                          const int64_t* win_lo, const int64_t* win_hi /* per contig, NULL = everything */) {
     if (L < 1 || L > 32 || n < 0 || n_threads < 1 || gcap < 0 || gcap > 3) return -2;
     pexpr_t x;
     memset(&x, 0, sizeof x);
@@ -678,6 +722,7 @@ int oracle_screen_pattern(const char* seq, const int64_t* offsets, int n_contigs
             j->counts = counts_out;
             j->pamless = pamless; j->n5 = n5; j->n3 = n3; j->max5 = max5; j->max3 = max3;
             j->len5 = len5; j->allow5 = allow5; j->len3 = len3; j->allow3 = allow3;
+            j->wlo = win_lo ? win_lo[c] : -(int64_t)L - 8; j->whi = win_hi ? win_hi[c] : len + 8;
             pthread_create(&th[t], NULL, p_run, j);
         }
         for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);

@@ -167,3 +167,33 @@ def test_bitsliced_cpu_port_equals_the_scalar_oracle():
             b = c_oracle.screen_hamming_arrays(blob, off, masks, grnas, M, 3, ranges, bitsliced=True)
             assert a.tolist() == b.tolist(), (L, M, ranges)
         assert a.sum() > 0
+
+
+def test_gapped_and_pattern_oracles_window_ranges_partition():
+    """win_ranges of oracle_screen_nopattern_win / oracle_screen_pattern (the C side of mg_screen's window shards for the
+    general path): an anchor belongs to the window it ends at, so the counts of a partition of the window starts add up to
+    the whole, on both strands, across masks and contig ends."""
+    rng = random.Random(4)
+    contigs = [("a", "".join(rng.choice("ACGT" * 8 + "N") for _ in range(3000))), ("b", "".join(rng.choice("ACGT") for _ in range(900)))]
+    grnas = []
+    for i in range(24):
+        _, seq = contigs[i % 2]
+        p = rng.randrange(0, len(seq) - 22)
+        s = list(seq[p:p + 20].replace("N", "T"))
+        for _ in range(i % 3):
+            s[rng.randrange(20)] = rng.choice("ACGT")
+        if i % 3 == 0:
+            k = rng.randrange(2, 18)
+            s = s[:k] + s[k + 1:] + [rng.choice("ACGT")]
+        s = "".join(s)
+        grnas.append(O.reverse_complement(s) if i % 4 == 1 else s)
+    masks = [(0, 100, 160)]
+    cuts = [-40, 500, 501, 1777, 3100]
+    parts = [[(a, b), (a - 200, b - 200)] for a, b in zip(cuts[:-1], cuts[1:])]
+    full = c_oracle.screen_nopattern(contigs, masks, grnas, 2, 1, threads=2)
+    assert full.sum() > 10
+    assert sum(c_oracle.screen_nopattern(contigs, masks, grnas, 2, 1, threads=2, win_ranges=r) for r in parts).tolist() == full.tolist()
+    for pat, gap in (("1mg1-", 2), ("0mg-10,1mg-11-", 2), ("1m-8,2m9-", 0)):
+        full = c_oracle.screen_pattern(contigs, masks, grnas, pat, gap, threads=2)
+        assert full.sum() > 0
+        assert sum(c_oracle.screen_pattern(contigs, masks, grnas, pat, gap, threads=2, win_ranges=r) for r in parts).tolist() == full.tolist(), pat
