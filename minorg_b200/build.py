@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libminorg_b200.so")
-SOURCES = ["genome.cu", "queries.cu", "screen_bitsliced.cu", "screen_general.cu", "screen_gapped.cu", "enumerate.cu", "maskfind.cu", "fasta_io.cu", "api.cu"]
+SOURCES = ["genome.cu", "queries.cu", "screen_bitsliced.cu", "screen_general.cu", "screen_gapped.cu", "screen_seedjoin.cu", "enumerate.cu", "maskfind.cu", "fasta_io.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 

@@ -104,6 +104,11 @@ __device__ __forceinline__ bool span_masked(const GenomeView& g, int64_t a, int6
 
 }  // namespace mg
 
+namespace mg {
+struct SeedIndex;                         // half-gRNA hash index of the seed-and-join screen (screen_seedjoin.cu), built on first use
+void seed_index_free(SeedIndex* ix);
+}
+
 // Concrete handle types behind the opaque C names.
 struct mg_genome {
     int device = 0;
@@ -142,6 +147,7 @@ struct mg_queries {
     uint32_t* d_tab2 = nullptr;
     uint4* d_packed = nullptr;
     cudaStream_t stream = nullptr;          // the creating stream; the tables are freed in its order
+    mutable mg::SeedIndex* sj = nullptr;    // lazily built by launch_seedjoin
     mg::QueriesView view() const {
         mg::QueriesView v;
         v.codes = d_codes; v.tab = d_tab; v.tab2 = d_tab2; v.packed = d_packed; v.n = n; v.len = len; v.n_groups = n_groups;

@@ -131,6 +131,7 @@ int mg_queries_length(const mg_queries* q) { return q ? q->len : 0; }
 
 void mg_queries_free(mg_queries* q) {
     if (!q) return;
+    mg::seed_index_free(q->sj);
     dev_free(q->d_codes, q->stream); dev_free(q->d_tab, q->stream); dev_free(q->d_tab2, q->stream); dev_free(q->d_packed, q->stream);
     delete q;
 }

@@ -34,6 +34,8 @@
 // The bottom-row score is a bit-sliced up/down counter biased so that "score <= K" is the complement of its top bit.
 // A thread owns a run of consecutive text characters (plus L+K warm-up characters: a match of cost <= K spans at
 // most L+K characters) and walks it once per query group; survivors are queued for the exact verifier.
+#include <algorithm>
+
 #include "common.cuh"
 #include "verify.cuh"
 
@@ -124,7 +126,7 @@ struct RowsState {
 template <int L, int NF>
 __global__ void __launch_bounds__(RowsThreads<L>::value, 1)
 gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ tabr, const GeneralCtx* __restrict__ ctx,
-                   int K, int strand, int groups_per_chunk, int g_begin, int g_end, int64_t eb, int64_t ee, int run,
+                   int K, int strand, int groups_per_chunk, int groups_per_cta, int g_begin, int g_end, int64_t eb, int64_t ee, int run,
                    uint32_t one, uint32_t minus_one) {
     constexpr int LP = (L + 3) / 4 * 4;                // rows padded to whole 128-bit loads
     constexpr int SG = kRowsCodes * LP;                // words per group: [code][row]
@@ -146,6 +148,9 @@ gapped_rows_kernel(GenomeView gv, QueriesView qv, const uint32_t* __restrict__ t
     const int64_t p_begin = max((int64_t)0, p_first - warm);       // the initial column is exact at the start of the text
     const int64_t e_base = eb - 1 + (int64_t)blockIdx.x * kRowsThreads * run - warm;   // <= every anchor this CTA reports
     if (threadIdx.x == 0) cq_count = 0u;
+    // a short text range with many gRNA groups is cut over blockIdx.y by GROUP range (groups_per_cta each)
+    g_begin += (int)blockIdx.y * groups_per_cta;
+    g_end = min(g_end, g_begin + groups_per_cta);
 
     for (int cg = g_begin; cg < g_end; cg += groups_per_chunk) {
         const int ng = min(groups_per_chunk, g_end - cg);
@@ -222,11 +227,8 @@ static int launch_rows(const mg_genome* g, const mg_queries* q, const uint32_t* 
     constexpr int kRowsThreads = RowsThreads<L>::value;
     const int max_groups = (smem_max - 1024 - kRowsQueue * 8) / (SG * 4);
     const int n_groups = g_end - g_begin;
-    const int gpc = n_groups < max_groups ? n_groups : max_groups;
-    const size_t smem = (size_t)gpc * SG * 4 + (size_t)kRowsQueue * 8;       // tables, then the survivor queue
     static const bool alu_only = [] { const char* e = getenv("MG_ROWS"); return e && strcmp(e, "alu") == 0; }();   // A/B: all five ops as LOP3
     auto kern = alu_only ? gapped_rows_kernel<L, 0> : gapped_rows_kernel<L, L>;
-    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_anchor = ee - eb;
     // characters per thread: long enough to amortise the L+K warm-up, short enough to fill the machine; whole waves of
     // CTAs (one CTA per SM), and a multiple of 16 so that every lane of a warp sits at the same offset inside its
@@ -236,10 +238,23 @@ static int launch_rows(const mg_genome* g, const mg_queries* q, const uint32_t* 
     int64_t run = (n_anchor + per_wave * waves - 1) / (per_wave * waves);
     if (run < 64) run = 64;
     run = (run + 15) / 16 * 16;
-    const int64_t threads = (n_anchor + run - 1) / run;
-    const unsigned grid = (unsigned)((threads + kRowsThreads - 1) / kRowsThreads);
-    kern<<<grid, kRowsThreads, smem, s>>>(g->view(), q->view(), d_tab, d_ctx, K, strand, gpc, g_begin, g_end, eb, ee, (int)run,
-                                          1u, 0xFFFFFFFFu);
+    // A short text range (the dirty ranges the seed-and-join screen leaves to this path: ~10^2 windows around a contig end or
+    // an N run) cannot fill the machine with text: shorter runs, and the gRNA groups are cut over blockIdx.y instead.
+    int64_t threads = (n_anchor + run - 1) / run;
+    unsigned grid = (unsigned)((threads + kRowsThreads - 1) / kRowsThreads);
+    int gy = 1;
+    if ((int)grid * 2 <= sms && n_groups > 32) {
+        if (threads < 64) { run = 16; threads = (n_anchor + run - 1) / run; grid = (unsigned)((threads + kRowsThreads - 1) / kRowsThreads); }
+        gy = std::min((n_groups + 15) / 16, (4 * sms + (int)grid - 1) / (int)grid);
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+    }
+    const int groups_per_cta = (n_groups + gy - 1) / gy;
+    const int gpc = groups_per_cta < max_groups ? groups_per_cta : max_groups;
+    const size_t smem = (size_t)gpc * SG * 4 + (size_t)kRowsQueue * 8;       // tables, then the survivor queue
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(grid, (unsigned)gy, 1), kRowsThreads, smem, s>>>(g->view(), q->view(), d_tab, d_ctx, K, strand, gpc, groups_per_cta, g_begin,
+                                                                   g_end, eb, ee, (int)run, 1u, 0xFFFFFFFFu);
     MG_CUDA(cudaGetLastError());
     return MG_OK;
 }

@@ -19,6 +19,9 @@ int launch_screen_bitsliced_general(const mg_genome* g, const mg_queries* q, int
                                     int64_t wb, int64_t we, uint32_t* d_counts, cudaStream_t s);
 int launch_gapped_rows(const mg_genome* g, const mg_queries* q, const GeneralCtx* d_ctx, int K, int strand, int g_begin,
                        int g_end, int64_t eb, int64_t ee, uint32_t** d_tab_cache, cudaStream_t s);
+bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit);
+int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const GeneralCtx* d_ctx, int64_t wb, int64_t we,
+                    uint32_t* d_counts, cudaStream_t s, std::vector<std::pair<int64_t, int64_t>>& dirty_ranges);
 
 // ----------------------------------------------------------------------------------------- Myers <= K
 constexpr int kMyersThreads = 128;     // gRNA per CTA (one per thread; a warp shares the text character)
@@ -418,10 +421,31 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
                 out.push_back(Slice{r.a + len * j / tparts, r.a + len * (j + 1) / tparts,
                                     (int)(r.g0 + ng * i / gparts), (int)(r.g0 + ng * (i + 1) / gparts)});
     };
+    unsigned long long total_cand = 0;
+    int n_slices = 0;
+    const bool trace = getenv("MG_TRACE") != nullptr;      // adds a synchronisation per slice to time the two passes
+    double t_prefilter = 0.0, t_verify = 0.0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     std::vector<Slice> todo;
     Slice rest{0, 0, 0, 0};
     bool have_rest = false;
-    {   // a small probe slice first: its survivor density sizes the remaining slices, so that an overflow (a wasted
+    // Large gRNA sets under the one-gap no-pattern criterion: the seed-and-join screen (screen_seedjoin.cu) counts every anchor
+    // whose neighbourhood is free of invalid bases; what is left for the prefilter + verifier below are the short "dirty" window
+    // ranges around contig ends and N runs.
+    bool seedjoin_done = false;
+    if (!no_prefilter && by_myers && use_rows && seedjoin_eligible(q, crit)) {
+        std::vector<std::pair<int64_t, int64_t>> dirty;
+        const double t0 = trace ? now() : 0.0;
+        const int r2 = launch_seedjoin(g, q, crit, d_ctx, wb, we, d_counts, s, dirty);
+        if (r2 == MG_OK) {
+            seedjoin_done = true;
+            for (auto it = dirty.rbegin(); it != dirty.rend(); ++it) todo.push_back(Slice{it->first, it->second, 0, n_query_groups});
+            if (trace) { cudaStreamSynchronize(s); fprintf(stderr, "[mg_screen general] seed-and-join %.1f ms, %zu dirty window ranges left to the DP path\n", (now() - t0) * 1e3, dirty.size()); }
+        } else if (r2 != MG_ERR_UNSUPPORTED) {
+            rc = r2;
+        }
+    }
+    if (!seedjoin_done && rc == MG_OK) {   // a small probe slice first: its survivor density sizes the remaining slices, so that an overflow (a wasted
         // prefilter pass) only happens when the density is very uneven
         const int64_t len = we - wb, probe = len / 64;
         int64_t probe_min = 1 << 16;
@@ -434,11 +458,6 @@ int launch_screen_general(const mg_genome* g, const mg_queries* q, const mg_crit
             todo.push_back(Slice{wb, we, 0, n_query_groups});
         }
     }
-    unsigned long long total_cand = 0;
-    int n_slices = 0;
-    const bool trace = getenv("MG_TRACE") != nullptr;      // adds a synchronisation per slice to time the two passes
-    double t_prefilter = 0.0, t_verify = 0.0;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (!todo.empty() && rc == MG_OK) {
         const Slice r = todo.back();
         todo.pop_back();

@@ -1,0 +1,474 @@
+// K7: seed-and-join screen for the no-pattern ONE-GAP criterion on LARGE gRNA sets (the north star's job: 10^6 gRNA,
+// <= 4 mismatches / <= 1 gap).  Replaces, for that criterion, the bit-sliced edit-distance DP of screen_gapped.cu, which has
+// to touch every (gRNA, text position, DP row): 182 issue slots per 32 cells whatever the data.
+//
+// Criterion (MINORg.py:2018-2044 with ot_gap = 2, no pattern, PAM-less): an anchor (gRNA, strand, virtual end e) is
+// problematic iff some alignment ending there has  mm <= M, gaps <= 1, mm + gaps + unaligned <= M + 1.  For a window whose
+// neighbourhood holds only valid bases (everything else goes to the DP path, see "dirty" below) that is equivalent to
+//     ungapped : Hamming h <= M, or h == M + 1 with a mismatch at an end position (trim it: mm = M, unaligned = 1), or
+//     deletion : min over k = 1..19 of  #mm(query[0,k) on diagonal w-1) + #mm(query[k,20) on diagonal w)      <= M, or
+//     insertion: min over k = 1..18 of  #mm(query[0,k) on diagonal w+1) + #mm(query[k+1,20) on diagonal w)    <= M
+// (with a gap, trimming a position costs what the mismatch it removes cost, so the full-length alignment decides).
+//
+// Pigeonhole.  Cut the gRNA into halves H1 = [0,10), H2 = [10,20), t = floor((M+1)/2), g = M - t - 1.  Every alignment that
+// satisfies the criterion has a gap-free half with <= t mismatches, or its gapped half has <= g mismatches:
+//     R1  H2 on the final diagonal w            with <= t mismatches      R2  H1 on w       with <= t
+//     R3  H1 on w-1 (a deletion follows)        with <= t                 R4  H1 on w+1 (an insertion follows) with <= t
+//     R5  H1 with a deletion before k = 1..9    and <= g mismatches       R6  H1 with an insertion at k = 1..9, <= g
+//     R7  H2 with a deletion before k = 11..19  and <= g                  R8  H2 with an insertion at k = 10..18, <= g
+// So instead of asking every gRNA about every position, every text position asks two hash tables (gRNA by H1, gRNA by H2,
+// direct-addressed by the 20-bit 10-mer) for the gRNA whose half equals one of the strings the text can produce: the
+// Hamming-<=t neighbours of the 10-mer at p (R1-R4), the 11-mer at p with one inner base removed and <= g substitutions
+// (R5, R7), the 9-mer at p with one base inserted and <= g substitutions (R6, R8): ~1 800 keys per position and strand,
+// independent of the number of gRNA; at 10^6 gRNA ~0.95 candidates per key, i.e. 3.5e-3 of the cells are looked at, each
+// with ~25 instructions (three diagonal mismatch masks from bit planes held in registers, one route-specific necessary
+// test), and ~4 % of those with the exact evaluation above.
+//
+// Exactly-once counting.  An anchor can be reached through several routes and variants (from different threads).  Where no
+// mask is near, it is counted by the route that the CANONICAL alignment (ungapped if it fits, else the deletion with the
+// smallest k, else the insertion with the smallest k) implies: its gap-free half if that has <= t mismatches (H2 first),
+// else its gapped half with that k.  Where a masked (on-target) interval is near, "problematic" also depends on spans, so
+// the exact verifier of the DP path decides (verify_anchor) and the anchor belongs to the FIRST applicable route in the
+// order R1..R8 (smallest k inside a gapped route).  Both rules are functions of (gRNA, anchor) only, so every thread that
+// reaches the anchor agrees on who counts it.
+//
+// Dirty windows.  A window whose bases [w-3, w+23) touch a 32-base block with an invalid base (N, IUPAC, contig padding,
+// i.e. also everything that hangs off a contig end) is left to the DP path: the host collects those blocks, merges them
+// into window ranges and runs the prefilter + verifier on them.  Both paths use the same predicate, so every anchor is
+// owned by exactly one of them.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "verify.cuh"
+
+namespace mg {
+
+constexpr int kSjL = 20;
+constexpr uint32_t kSjKeys = 1u << 20;               // 4^10 half keys
+constexpr uint32_t kH1M = 0x3FFu, kH2M = 0xFFC00u, kFull = 0xFFFFFu;
+
+struct SeedIndex {
+    uint32_t* d_start[2] = {nullptr, nullptr};       // [kSjKeys + 1] first entry of each key, gRNA by H1 / by H2
+    uint2* d_entries[2] = {nullptr, nullptr};        // [n] {query bit planes, gRNA index}
+    int n = 0;
+    bool usable = false;                             // false: some gRNA has a non-ACGT base (it stays with the DP path)
+    cudaStream_t stream = nullptr;
+};
+
+struct SeedIndexView {
+    const uint32_t* start[2];
+    const uint2* entries[2];
+};
+
+void seed_index_free(SeedIndex* ix) {
+    if (!ix) return;
+    for (int h = 0; h < 2; ++h) { dev_free(ix->d_start[h], ix->stream); dev_free(ix->d_entries[h], ix->stream); }
+    delete ix;
+}
+
+// ------------------------------------------------------------------------------------------------ index
+__device__ __forceinline__ void sj_keys(const uint4 p, uint32_t& k1, uint32_t& k2) {
+    k1 = p.x & kFull;                                 // positions 0..9, 2 bits each
+    k2 = ((p.x >> 20) | (p.y << 12)) & kFull;         // positions 10..19
+}
+
+__global__ void sj_count_kernel(const uint4* __restrict__ packed, int n, uint32_t* __restrict__ cnt1, uint32_t* __restrict__ cnt2,
+                                unsigned int* __restrict__ n_invalid) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint4 p = packed[q];
+    if (p.z & kFull) { atomicAdd(n_invalid, 1u); return; }
+    uint32_t k1, k2;
+    sj_keys(p, k1, k2);
+    atomicAdd(cnt1 + k1, 1u);
+    atomicAdd(cnt2 + k2, 1u);
+}
+
+__global__ void sj_fill_kernel(const uint4* __restrict__ packed, int n, uint32_t* __restrict__ cur1, uint32_t* __restrict__ cur2,
+                               uint2* __restrict__ e1, uint2* __restrict__ e2) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint4 p = packed[q];
+    if (p.z & kFull) return;
+    uint32_t k1, k2;
+    sj_keys(p, k1, k2);
+    const uint32_t qlo = compress_even(p.x, p.y) & kFull, qhi = compress_even(p.x >> 1, p.y >> 1) & kFull;   // bit j = low / high code bit of position j
+    const uint2 e = make_uint2(qlo | (qhi << 20), (qhi >> 12) | ((uint32_t)q << 8));
+    e1[atomicAdd(cur1 + k1, 1u)] = e;
+    e2[atomicAdd(cur2 + k2, 1u)] = e;
+}
+
+static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out) {
+    SeedIndex* ix = new SeedIndex();
+    ix->n = q->n;
+    ix->stream = s;
+    *out = ix;
+    const size_t kb = sizeof(uint32_t) * ((size_t)kSjKeys + 1);
+    uint32_t* d_cur[2] = {nullptr, nullptr};
+    unsigned int* d_bad = nullptr;
+    std::vector<uint32_t> h((size_t)kSjKeys + 1);
+    cudaError_t e = cudaSuccess;
+    do {
+        for (int t = 0; t < 2 && e == cudaSuccess; ++t) {
+            e = dev_alloc((void**)&ix->d_start[t], kb, s);
+            if (e == cudaSuccess) e = dev_alloc((void**)&ix->d_entries[t], sizeof(uint2) * (size_t)std::max(1, q->n), s);
+            if (e == cudaSuccess) e = dev_alloc((void**)&d_cur[t], kb, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_cur[t], 0, kb, s);
+        }
+        if (e != cudaSuccess) break;
+        if ((e = dev_alloc((void**)&d_bad, 4, s)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(d_bad, 0, 4, s)) != cudaSuccess) break;
+        const int grid = (q->n + 255) / 256;
+        if (grid) sj_count_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, d_cur[0], d_cur[1], d_bad);
+        unsigned int bad = 0;
+        if ((e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        for (int t = 0; t < 2 && e == cudaSuccess; ++t) {
+            // exclusive scan on the host: 4 MB per table, once per gRNA set
+            if ((e = cudaMemcpyAsync(h.data(), d_cur[t], kb, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+            uint32_t run = 0;
+            for (size_t k = 0; k <= kSjKeys; ++k) { const uint32_t c = h[k]; h[k] = run; run += c; }
+            if ((e = cudaMemcpyAsync(ix->d_start[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_cur[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) break;
+        ix->usable = bad == 0;
+        if (ix->usable && grid) sj_fill_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, d_cur[0], d_cur[1], ix->d_entries[0], ix->d_entries[1]);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    } while (0);
+    dev_free(d_cur[0], s); dev_free(d_cur[1], s); dev_free(d_bad, s);
+    if (e != cudaSuccess) { set_error("seed index: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+struct SjParams {
+    int N, M, t, g;            // gRNA count, mismatch budget, pigeonhole thresholds
+    int strand;
+    int64_t wb, we;            // forward window starts owned by this call
+};
+
+struct SjText {
+    uint32_t tlo0, tlo1, thi0, thi1;   // bit planes of the 64 strand bases from p - 12 (bit i of word 0 = base p - 12 + i)
+    uint32_t okmask, nearmask;         // per candidate window wi = 0..12 (w = p - 11 + wi): owned and clean / a mask is near
+    int64_t p;
+};
+
+// 32 bases of the strand's text from strand position x0, as 2-bit codes (base i at bits 2i of hi:lo)
+__device__ __forceinline__ void sj_load32(const GenomeView& gv, int strand, int64_t x0, uint32_t& lo, uint32_t& hi) {
+    uint32_t inv;
+    if (strand > 0) { load_window(gv, x0, lo, hi, inv); return; }
+    uint32_t flo, fhi;
+    load_window(gv, gv.glen - x0 - 32, flo, fhi, inv);
+    auto rev2 = [](uint32_t v) { v = __brev(v); return ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); };
+    lo = ~rev2(fhi);
+    hi = ~rev2(flo);
+}
+
+// forward window start of the strand window w (20 bases from strand position w)
+__device__ __forceinline__ int64_t sj_fwd_window(const GenomeView& gv, int strand, int64_t w) { return strand > 0 ? w : gv.glen - w - kSjL; }
+
+// the window's bases [w-3, w+23) (forward) touch a 32-base block holding an invalid base
+__device__ __forceinline__ bool sj_dirty(const GenomeView& gv, int64_t wf) {
+    if (wf < 3 || wf + 23 > gv.glen) return true;
+    return (__ldg(gv.invalid + ((wf - 3) >> 5)) | __ldg(gv.invalid + ((wf + 22) >> 5))) != 0u;
+}
+
+// some masked interval meets [a, b)
+__device__ __forceinline__ bool sj_mask_near(const GenomeView& gv, int64_t a, int64_t b) {
+    int lo = 0, hi = gv.n_masks - 1, ans = -1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        if (gv.mstart[mid] < b) { ans = mid; lo = mid + 1; } else hi = mid - 1;
+    }
+    return ans >= 0 && gv.mend_pm[ans] > a;
+}
+
+__device__ __forceinline__ uint32_t sj_diag(const SjText& T, uint32_t qlo, uint32_t qhi, int o) {
+    const uint32_t tl = __funnelshift_r(T.tlo0, T.tlo1, (unsigned)o), th = __funnelshift_r(T.thi0, T.thi1, (unsigned)o);
+    return ((tl ^ qlo) | (th ^ qhi)) & kFull;        // bit j: query position j mismatches the text at offset o + j
+}
+
+// The canonical alignment of a clean, unmasked anchor and the route it implies (0: the anchor is not problematic).
+__device__ __noinline__ int sj_canonical(uint32_t D0, uint32_t DM, uint32_t DP, int M, int t, int& kq) {
+    const int h = __popc(D0), c2 = __popc(D0 & kH2M);
+    kq = 0;
+    if (h <= M || (h == M + 1 && (D0 & 0x80001u))) return c2 <= t ? 1 : 2;
+    int a = 0, b = h;                                 // deletion before k: #mm(DM, [0,k)) + #mm(D0, [k,20))
+    for (int k = 1; k <= 19; ++k) {
+        a += (int)((DM >> (k - 1)) & 1u);
+        b -= (int)((D0 >> (k - 1)) & 1u);
+        if (a + b <= M) {
+            kq = k;
+            if (k <= 9) return c2 <= t ? 1 : 5;
+            if (k == 10) return c2 <= t ? 1 : 3;
+            return __popc(DM & kH1M) <= t ? 3 : 7;
+        }
+    }
+    a = 0; b = h - (int)(D0 & 1u);                    // insertion at k: #mm(DP, [0,k)) + #mm(D0, [k+1,20))
+    for (int k = 1; k <= 18; ++k) {
+        a += (int)((DP >> (k - 1)) & 1u);
+        b -= (int)((D0 >> k) & 1u);
+        if (a + b <= M) {
+            kq = k;
+            if (k <= 9) return c2 <= t ? 1 : 6;
+            return __popc(DP & kH1M) <= t ? 4 : 8;
+        }
+    }
+    return 0;
+}
+
+// First applicable route in the order R1..R8 (mask-near anchors), with the smallest k of a gapped route.
+__device__ __noinline__ int sj_first_applicable(uint32_t D0, uint32_t DM, uint32_t DP, int t, int g, int& kq) {
+    kq = 0;
+    if (__popc(D0 & kH2M) <= t) return 1;
+    if (__popc(D0 & kH1M) <= t) return 2;
+    if (__popc(DM & kH1M) <= t) return 3;
+    if (__popc(DP & kH1M) <= t) return 4;
+    if (g < 0) return 0;
+    for (int k = 1; k <= 9; ++k) { const uint32_t lowk = (1u << k) - 1u; if (__popc(DM & lowk) + __popc(D0 & kH1M & ~lowk) <= g) { kq = k; return 5; } }
+    for (int k = 1; k <= 9; ++k) { const uint32_t lowk = (1u << k) - 1u, lowk1 = (2u << k) - 1u; if (__popc(DP & lowk) + __popc(D0 & kH1M & ~lowk1) <= g) { kq = k; return 6; } }
+    for (int k = 11; k <= 19; ++k) { const uint32_t lowk = (1u << k) - 1u; if (__popc(DM & kH2M & lowk) + __popc(D0 & kFull & ~lowk) <= g) { kq = k; return 7; } }
+    for (int k = 10; k <= 18; ++k) { const uint32_t lowk = (1u << k) - 1u, lowk1 = (2u << k) - 1u; if (__popc(DP & kH2M & lowk) + __popc(D0 & kFull & ~lowk1) <= g) { kq = k; return 8; } }
+    return 0;
+}
+
+// One candidate (gRNA id, query planes) reached through route r (k_probe: gap position in query coordinates for r >= 5)
+// at candidate window wi: count the anchor if it is problematic and this (route, k) owns it.
+__device__ __forceinline__ void sj_anchor(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
+                                          const SjText& T, int wi, int r, int k_probe, uint32_t id, uint32_t qlo, uint32_t qhi,
+                                          uint32_t* __restrict__ counts) {
+    if (!((T.okmask >> wi) & 1u)) return;
+    const int o = wi + 1, M = prm.M, t = prm.t;
+    const bool near = (T.nearmask >> wi) & 1u;
+    const uint32_t D0 = sj_diag(T, qlo, qhi, o);
+    // Necessary conditions for "the canonical alignment of a problematic anchor implies route r" (cheap; a few per cent pass).
+    // An insertion skips one query position, so bounds that use "mismatches on both diagonals" get one unit of slack.
+    if (!near) {
+        if (r == 2 && __popc(D0) > M + 1) return;                              // R2 only owns ungapped alignments
+        if ((r == 5 || r == 6) && __popc(D0 & kH2M) > M) return;              // H2 is gap-free on the final diagonal
+    }
+    const uint32_t DM = sj_diag(T, qlo, qhi, o - 1), DP = sj_diag(T, qlo, qhi, o + 1);
+    const int64_t w = T.p - 11 + wi;                  // strand window start of the final diagonal
+    int kq = 0;
+    if (near) {
+        const int owner = sj_first_applicable(D0, DM, DP, t, prm.g, kq);
+        if (owner != r || (r >= 5 && kq != k_probe)) return;
+        if (!verify_anchor(gv, *ctx, qv.codes + (size_t)id * kSjL, qv.packed + id, prm.strand, w + kSjL)) return;
+    } else {
+        if (r == 1) { if (min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) > M + 1) return; }
+        else if (r == 3) { if (__popc(DM & kH1M) + __popc(DM & D0 & kH2M) > M) return; }
+        else if (r == 4) { if (__popc(DP & kH1M) + __popc(DP & D0 & kH2M) > M + 1) return; }
+        else if (r == 7) { if (__popc(DM & kH1M) > M) return; }
+        else if (r == 8) { if (__popc(DP & kH1M) > M) return; }
+        const int owner = sj_canonical(D0, DM, DP, M, t, kq);
+        if (owner != r || (r >= 5 && kq != k_probe)) return;
+    }
+    atomicAdd(counts + (prm.strand > 0 ? id : (uint32_t)prm.N + id), 1u);
+}
+
+// every gRNA whose H1 (table 0) / H2 (table 1) equals `key`; cls 0 = gap-free half, 1 = deletion variant, 2 = insertion variant
+__device__ __forceinline__ void sj_probe(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
+                                         const SeedIndexView& ix, const SjText& T, uint32_t key, int cls, int k, uint32_t* __restrict__ counts) {
+#pragma unroll
+    for (int tbl = 0; tbl < 2; ++tbl) {
+        if (cls == 2 && (tbl == 0 ? k < 1 : k > 8)) continue;       // insertion at query position k (H1: 1..9) or 10 + k (H2: 10..18)
+        const uint32_t a = __ldg(ix.start[tbl] + key), b = __ldg(ix.start[tbl] + key + 1);
+        for (uint32_t i = a; i < b; ++i) {
+            const uint2 e = __ldg(ix.entries[tbl] + i);
+            const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, id = e.y >> 8;
+            if (tbl == 0) {
+                if (cls == 0) {
+                    sj_anchor(gv, qv, ctx, prm, T, 11, 2, 0, id, qlo, qhi, counts);     // H1 on the final diagonal: w = p
+                    sj_anchor(gv, qv, ctx, prm, T, 12, 3, 0, id, qlo, qhi, counts);     // H1 on w - 1: w = p + 1
+                    sj_anchor(gv, qv, ctx, prm, T, 10, 4, 0, id, qlo, qhi, counts);     // H1 on w + 1: w = p - 1
+                } else if (cls == 1) sj_anchor(gv, qv, ctx, prm, T, 12, 5, k, id, qlo, qhi, counts);
+                else sj_anchor(gv, qv, ctx, prm, T, 10, 6, k, id, qlo, qhi, counts);
+            } else {
+                if (cls == 0) sj_anchor(gv, qv, ctx, prm, T, 1, 1, 0, id, qlo, qhi, counts);          // H2 at p: w = p - 10
+                else if (cls == 1) sj_anchor(gv, qv, ctx, prm, T, 2, 7, 10 + k, id, qlo, qhi, counts); // w - 1 = p - 10
+                else sj_anchor(gv, qv, ctx, prm, T, 0, 8, 10 + k, id, qlo, qhi, counts);               // w + 1 = p - 10
+            }
+        }
+    }
+}
+
+// Variant table (the same for every text position): [19:0] substitution mask on the 20-bit key, [21:20] class
+// (0 gap-free half, 1 deletion, 2 insertion), [25:22] k, [27:26] inserted base.  One loop, one probe site: the 32 lanes of a
+// warp work on the same variant of 32 different text positions.
+static std::vector<uint32_t> sj_variants(int t, int g) {
+    std::vector<uint32_t> v;
+    auto push = [&](uint32_t mask, uint32_t cls, uint32_t k, uint32_t x) { v.push_back(mask | (cls << 20) | (k << 22) | (x << 26)); };
+    push(0, 0, 0, 0);
+    if (t >= 1)
+        for (int i = 0; i < 10; ++i)
+            for (uint32_t x = 1; x <= 3; ++x) {
+                push(x << (2 * i), 0, 0, 0);
+                if (t >= 2)
+                    for (int j = i + 1; j < 10; ++j)
+                        for (uint32_t y = 1; y <= 3; ++y) push((x << (2 * i)) | (y << (2 * j)), 0, 0, 0);
+            }
+    if (g < 0) return v;
+    for (uint32_t k = 1; k <= 9; ++k) {                     // deletion: the 11-mer at p without its base k
+        push(0, 1, k, 0);
+        if (g >= 1)
+            for (int s = 0; s < 10; ++s)
+                for (uint32_t x = 1; x <= 3; ++x) push(x << (2 * s), 1, k, 0);
+    }
+    for (uint32_t k = 0; k <= 9; ++k)                        // insertion: the 9-mer at p with base x inserted at k
+        for (uint32_t x = 0; x <= 3; ++x) {
+            push(0, 2, k, x);
+            if (g >= 1)
+                for (int s = 0; s < 10; ++s) {
+                    if (s == (int)k) continue;               // a substitution never touches the inserted base
+                    for (uint32_t y = 1; y <= 3; ++y) push(y << (2 * s), 2, k, x);
+                }
+        }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx* __restrict__ ctx, SjParams prm,
+               const uint32_t* __restrict__ variants, int n_variants, int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts) {
+    const int64_t p = p_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p_end) return;
+    SjText T;
+    T.p = p;
+    T.okmask = 0u;
+    T.nearmask = 0u;
+    for (int wi = 0; wi <= 12; ++wi) {
+        const int64_t wf = sj_fwd_window(gv, prm.strand, p - 11 + wi);
+        if (wf < prm.wb || wf >= prm.we || sj_dirty(gv, wf)) continue;
+        T.okmask |= 1u << wi;
+        if (gv.n_masks && sj_mask_near(gv, wf - 3, wf + 24)) T.nearmask |= 1u << wi;
+    }
+    if (T.okmask == 0u) return;
+    uint32_t lo0, hi0, lo1, hi1;
+    sj_load32(gv, prm.strand, p - 12, lo0, hi0);
+    sj_load32(gv, prm.strand, p + 20, lo1, hi1);
+    T.tlo0 = compress_even(lo0, hi0); T.thi0 = compress_even(lo0 >> 1, hi0 >> 1);
+    T.tlo1 = compress_even(lo1, hi1); T.thi1 = compress_even(lo1 >> 1, hi1 >> 1);
+    const unsigned long long W = (((unsigned long long)hi0 << 32) | lo0) >> 24;       // 2-bit codes from base p on (20 bases)
+    const uint32_t T10 = (uint32_t)W & kFull, U11 = (uint32_t)W & 0x3FFFFFu, S9 = (uint32_t)W & 0x3FFFFu;
+
+    for (int v = 0; v < n_variants; ++v) {
+        const uint32_t d = __ldg(variants + v);
+        const uint32_t mask = d & kFull;
+        const int cls = (int)((d >> 20) & 3u), k = (int)((d >> 22) & 15u);
+        uint32_t key;
+        if (cls == 0) {
+            key = T10 ^ mask;
+        } else if (cls == 1) {
+            // two equal neighbours give the same string whichever is removed: the first one (smaller k) stands for both
+            if (((U11 >> (2 * k)) & 3u) == ((U11 >> (2 * k - 2)) & 3u)) continue;
+            const uint32_t low = (1u << (2 * k)) - 1u;
+            key = ((U11 & low) | ((U11 >> (2 * k + 2)) << (2 * k))) ^ mask;
+        } else {
+            const uint32_t low = (1u << (2 * k)) - 1u, x = (d >> 26) & 3u;
+            key = ((S9 & low) | (x << (2 * k)) | ((S9 >> (2 * k)) << (2 * k + 2))) ^ mask;
+        }
+        sj_probe(gv, qv, ctx, prm, ix, T, key, cls, k, counts);
+    }
+}
+
+// 32-base blocks of [b0, b1) that hold an invalid base
+__global__ void sj_dirty_blocks_kernel(GenomeView gv, int64_t b0, int64_t b1, unsigned int cap, unsigned int* __restrict__ n_out,
+                                       int64_t* __restrict__ out) {
+    const int64_t b = b0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= b1) return;
+    if (__ldg(gv.invalid + b) != 0u) {
+        const unsigned int slot = atomicAdd(n_out, 1u);
+        if (slot < cap) out[slot] = b;
+    }
+}
+
+// Can this screen use the seed-and-join path?  (criterion class, gRNA length, set size; MG_GAPPED=dp|seedjoin overrides the size rule)
+bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
+    if (crit->n_units != 0 || crit->max_gap != 1 || !crit->pamless || q->len != kSjL) return false;
+    if (crit->max_mismatch < 0 || crit->max_mismatch > 4 || q->n < 1 || q->n >= (1 << 24)) return false;
+    const char* env = getenv("MG_GAPPED");
+    if (env && strcmp(env, "dp") == 0) return false;
+    if (env && strcmp(env, "seedjoin") == 0) return true;
+    long long min_n = 150000;                          // below this the bit-sliced DP is faster (the probes do not depend on N)
+    if (const char* m = getenv("MG_SEEDJOIN_MIN")) min_n = atoll(m);
+    return q->n >= min_n;
+}
+
+// Counts every CLEAN anchor owned by the windows [wb, we) and returns the DIRTY window ranges the caller must hand to the DP
+// path.  Returns MG_ERR_UNSUPPORTED (nothing counted) if the index cannot represent the gRNA set or the genome is too ragged.
+int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const GeneralCtx* d_ctx, int64_t wb, int64_t we,
+                    uint32_t* d_counts, cudaStream_t s, std::vector<std::pair<int64_t, int64_t>>& dirty_ranges) {
+    dirty_ranges.clear();
+    if (q->sj == nullptr) {
+        SeedIndex* ix = nullptr;
+        const int rc = seed_index_build(q, s, &ix);
+        q->sj = ix;
+        if (rc != MG_OK) return rc;
+    }
+    const SeedIndex* ix = q->sj;
+    if (!ix->usable) return MG_ERR_UNSUPPORTED;
+    const GenomeView gv = g->view();
+    // dirty 32-base blocks around the owned windows -> window ranges for the DP path
+    const int64_t b0 = std::max<int64_t>(0, (wb - 3) >> 5), b1 = std::min<int64_t>(g->glen >> 5, ((we + 22) >> 5) + 1);
+    const unsigned int cap = 1u << 20;
+    unsigned int* d_n = nullptr;
+    int64_t* d_blocks = nullptr;
+    MG_CUDA(dev_alloc((void**)&d_n, 4, s));
+    cudaError_t e = dev_alloc((void**)&d_blocks, sizeof(int64_t) * cap, s);
+    if (e != cudaSuccess) { dev_free(d_n, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_NOMEM; }
+    unsigned int n_dirty = 0;
+    std::vector<int64_t> blocks;
+    e = cudaMemsetAsync(d_n, 0, 4, s);
+    if (e == cudaSuccess && b1 > b0) {
+        sj_dirty_blocks_kernel<<<(unsigned)((b1 - b0 + 255) / 256), 256, 0, s>>>(gv, b0, b1, cap, d_n, d_blocks);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_dirty, d_n, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && n_dirty <= cap && n_dirty) {
+        blocks.resize(n_dirty);
+        e = cudaMemcpyAsync(blocks.data(), d_blocks, sizeof(int64_t) * n_dirty, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    dev_free(d_n, s); dev_free(d_blocks, s);
+    if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    if (n_dirty > cap) return MG_ERR_UNSUPPORTED;      // a very ragged subject: the DP path takes all of it
+    std::sort(blocks.begin(), blocks.end());
+    for (const int64_t b : blocks) {                   // windows w with [w-3, w+23) meeting block b: [32b - 22, 32b + 35)
+        const int64_t a = std::max(wb, 32 * b - 22), z = std::min(we, 32 * b + 35);
+        if (a >= z) continue;
+        if (!dirty_ranges.empty() && a <= dirty_ranges.back().second) dirty_ranges.back().second = std::max(dirty_ranges.back().second, z);
+        else dirty_ranges.emplace_back(a, z);
+    }
+    // (the >= 64 invalid bases before the first and after the last contig make the windows at both ends of the coordinate
+    // space dirty through their blocks, which is what sj_dirty assumes for wf < 3 and wf + 23 > glen)
+    SjParams prm;
+    prm.N = q->n; prm.M = crit->max_mismatch; prm.t = (prm.M + 1) / 2; prm.g = prm.M - prm.t - 1;
+    prm.wb = wb; prm.we = we;
+    SeedIndexView iv;
+    for (int t = 0; t < 2; ++t) { iv.start[t] = ix->d_start[t]; iv.entries[t] = ix->d_entries[t]; }
+    const std::vector<uint32_t> vars = sj_variants(prm.t, prm.g);
+    uint32_t* d_vars = nullptr;
+    MG_CUDA(dev_alloc((void**)&d_vars, sizeof(uint32_t) * vars.size(), s));
+    e = cudaMemcpyAsync(d_vars, vars.data(), sizeof(uint32_t) * vars.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);              // vars lives on this stack frame
+    if (e != cudaSuccess) { dev_free(d_vars, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    for (int z = 0; z < 2; ++z) {
+        prm.strand = z == 0 ? 1 : -1;
+        // strand windows of the owned forward windows, then the positions that can reach them (w - 1 .. w + 11)
+        const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
+        int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
+        if (p1 <= p0) continue;
+        sj_scan_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, s>>>(gv, q->view(), iv, d_ctx, prm, d_vars, (int)vars.size(), p0, p1, d_counts);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+    }
+    dev_free(d_vars, s);
+    if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    return MG_OK;
+}
+
+}  // namespace mg
