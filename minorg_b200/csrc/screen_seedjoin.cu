@@ -48,22 +48,31 @@ constexpr int kSjL = 20;
 constexpr uint32_t kSjKeys = 1u << 20;               // 4^10 half keys
 constexpr uint32_t kH1M = 0x3FFu, kH2M = 0xFFC00u, kFull = 0xFFFFFu;
 
+// Tables: 0 = gRNA by H1, 1 = gRNA by H2 (4^10 keys, one entry per gRNA); 2 / 3 = gRNA by H1 / H2 WITHOUT one of its positions
+// (4^9 keys, nine entries per gRNA: H1 without position k = 1..9, H2 without its position k = 0..8, i.e. query position 10 + k):
+// an insertion in the gRNA is found by asking for the text's 9-mer instead of trying every inserted base at every position.
+// Entry (8 B): [19:0] low-bit plane of the 20 query bases, [39:20] high-bit plane, [43:40] k (position inside the half),
+// [63:44] gRNA index (< 2^20).
+constexpr int kSjTables = 4;
+constexpr uint32_t kSjKeys9 = 1u << 18;
+__host__ __device__ constexpr uint32_t sj_table_keys(int t) { return t < 2 ? kSjKeys : kSjKeys9; }
+
 struct SeedIndex {
-    uint32_t* d_start[2] = {nullptr, nullptr};       // [kSjKeys + 1] first entry of each key, gRNA by H1 / by H2
-    uint2* d_entries[2] = {nullptr, nullptr};        // [n] {query bit planes, gRNA index}
+    uint32_t* d_start[kSjTables] = {nullptr, nullptr, nullptr, nullptr};   // [keys + 1] first entry of each key
+    uint2* d_entries[kSjTables] = {nullptr, nullptr, nullptr, nullptr};
     int n = 0;
-    bool usable = false;                             // false: some gRNA has a non-ACGT base (it stays with the DP path)
+    bool usable = false;                             // false: some gRNA has a non-ACGT base (the set stays with the DP path)
     cudaStream_t stream = nullptr;
 };
 
 struct SeedIndexView {
-    const uint32_t* start[2];
-    const uint2* entries[2];
+    const uint32_t* start[kSjTables];
+    const uint2* entries[kSjTables];
 };
 
 void seed_index_free(SeedIndex* ix) {
     if (!ix) return;
-    for (int h = 0; h < 2; ++h) { dev_free(ix->d_start[h], ix->stream); dev_free(ix->d_entries[h], ix->stream); }
+    for (int h = 0; h < kSjTables; ++h) { dev_free(ix->d_start[h], ix->stream); dev_free(ix->d_entries[h], ix->stream); }
     delete ix;
 }
 
@@ -72,31 +81,37 @@ __device__ __forceinline__ void sj_keys(const uint4 p, uint32_t& k1, uint32_t& k
     k1 = p.x & kFull;                                 // positions 0..9, 2 bits each
     k2 = ((p.x >> 20) | (p.y << 12)) & kFull;         // positions 10..19
 }
-
-__global__ void sj_count_kernel(const uint4* __restrict__ packed, int n, uint32_t* __restrict__ cnt1, uint32_t* __restrict__ cnt2,
-                                unsigned int* __restrict__ n_invalid) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const uint4 p = packed[q];
-    if (p.z & kFull) { atomicAdd(n_invalid, 1u); return; }
-    uint32_t k1, k2;
-    sj_keys(p, k1, k2);
-    atomicAdd(cnt1 + k1, 1u);
-    atomicAdd(cnt2 + k2, 1u);
+__device__ __forceinline__ uint32_t sj_remove(uint32_t key10, int k) {      // the 10-mer without its position k (18 bits)
+    const uint32_t low = (1u << (2 * k)) - 1u;
+    return (key10 & low) | ((key10 >> (2 * k + 2)) << (2 * k));
+}
+__device__ __forceinline__ uint2 sj_entry(const uint4 p, int q, int k) {
+    const uint32_t qlo = compress_even(p.x, p.y) & kFull, qhi = compress_even(p.x >> 1, p.y >> 1) & kFull;   // bit j = low / high code bit of position j
+    return make_uint2(qlo | (qhi << 20), (qhi >> 12) | ((uint32_t)k << 8) | ((uint32_t)q << 12));
 }
 
-__global__ void sj_fill_kernel(const uint4* __restrict__ packed, int n, uint32_t* __restrict__ cur1, uint32_t* __restrict__ cur2,
-                               uint2* __restrict__ e1, uint2* __restrict__ e2) {
+// fill == 0: count the entries of every key (cur = counters); fill == 1: cur = running cursors, write the entries
+__global__ void sj_index_kernel(const uint4* __restrict__ packed, int n, int fill, uint32_t* __restrict__ cur0, uint32_t* __restrict__ cur1,
+                                uint32_t* __restrict__ cur2, uint32_t* __restrict__ cur3, uint2* __restrict__ e0, uint2* __restrict__ e1,
+                                uint2* __restrict__ e2, uint2* __restrict__ e3, unsigned int* __restrict__ n_invalid) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const uint4 p = packed[q];
-    if (p.z & kFull) return;
+    if (p.z & kFull) { if (!fill) atomicAdd(n_invalid, 1u); return; }
     uint32_t k1, k2;
     sj_keys(p, k1, k2);
-    const uint32_t qlo = compress_even(p.x, p.y) & kFull, qhi = compress_even(p.x >> 1, p.y >> 1) & kFull;   // bit j = low / high code bit of position j
-    const uint2 e = make_uint2(qlo | (qhi << 20), (qhi >> 12) | ((uint32_t)q << 8));
-    e1[atomicAdd(cur1 + k1, 1u)] = e;
-    e2[atomicAdd(cur2 + k2, 1u)] = e;
+    uint32_t s = atomicAdd(cur0 + k1, 1u);
+    if (fill) e0[s] = sj_entry(p, q, 0);
+    s = atomicAdd(cur1 + k2, 1u);
+    if (fill) e1[s] = sj_entry(p, q, 0);
+    for (int k = 1; k <= 9; ++k) {                    // H1 without position k: an insertion at query position k
+        s = atomicAdd(cur2 + sj_remove(k1, k), 1u);
+        if (fill) e2[s] = sj_entry(p, q, k);
+    }
+    for (int k = 0; k <= 8; ++k) {                    // H2 without its position k: an insertion at query position 10 + k
+        s = atomicAdd(cur3 + sj_remove(k2, k), 1u);
+        if (fill) e3[s] = sj_entry(p, q, k);      // 4-bit field: the position inside H2
+    }
 }
 
 static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out) {
@@ -104,15 +119,15 @@ static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out
     ix->n = q->n;
     ix->stream = s;
     *out = ix;
-    const size_t kb = sizeof(uint32_t) * ((size_t)kSjKeys + 1);
-    uint32_t* d_cur[2] = {nullptr, nullptr};
+    uint32_t* d_cur[kSjTables] = {nullptr, nullptr, nullptr, nullptr};
     unsigned int* d_bad = nullptr;
     std::vector<uint32_t> h((size_t)kSjKeys + 1);
     cudaError_t e = cudaSuccess;
     do {
-        for (int t = 0; t < 2 && e == cudaSuccess; ++t) {
+        for (int t = 0; t < kSjTables && e == cudaSuccess; ++t) {
+            const size_t kb = sizeof(uint32_t) * ((size_t)sj_table_keys(t) + 1);
             e = dev_alloc((void**)&ix->d_start[t], kb, s);
-            if (e == cudaSuccess) e = dev_alloc((void**)&ix->d_entries[t], sizeof(uint2) * (size_t)std::max(1, q->n), s);
+            if (e == cudaSuccess) e = dev_alloc((void**)&ix->d_entries[t], sizeof(uint2) * (size_t)std::max(1, q->n) * (t < 2 ? 1 : 9), s);
             if (e == cudaSuccess) e = dev_alloc((void**)&d_cur[t], kb, s);
             if (e == cudaSuccess) e = cudaMemsetAsync(d_cur[t], 0, kb, s);
         }
@@ -120,26 +135,29 @@ static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out
         if ((e = dev_alloc((void**)&d_bad, 4, s)) != cudaSuccess) break;
         if ((e = cudaMemsetAsync(d_bad, 0, 4, s)) != cudaSuccess) break;
         const int grid = (q->n + 255) / 256;
-        if (grid) sj_count_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, d_cur[0], d_cur[1], d_bad);
+        if (grid) sj_index_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, 0, d_cur[0], d_cur[1], d_cur[2], d_cur[3], nullptr, nullptr, nullptr, nullptr, d_bad);
         unsigned int bad = 0;
         if ((e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
-        for (int t = 0; t < 2 && e == cudaSuccess; ++t) {
-            // exclusive scan on the host: 4 MB per table, once per gRNA set
+        for (int t = 0; t < kSjTables && e == cudaSuccess; ++t) {
+            // exclusive scan on the host: <= 4 MB per table, once per gRNA set
+            const size_t nk = (size_t)sj_table_keys(t) + 1, kb = sizeof(uint32_t) * nk;
             if ((e = cudaMemcpyAsync(h.data(), d_cur[t], kb, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
             uint32_t run = 0;
-            for (size_t k = 0; k <= kSjKeys; ++k) { const uint32_t c = h[k]; h[k] = run; run += c; }
+            for (size_t k = 0; k < nk; ++k) { const uint32_t c = h[k]; h[k] = run; run += c; }
             if ((e = cudaMemcpyAsync(ix->d_start[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
             if ((e = cudaMemcpyAsync(d_cur[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
         }
         if (e != cudaSuccess) break;
         ix->usable = bad == 0;
-        if (ix->usable && grid) sj_fill_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, d_cur[0], d_cur[1], ix->d_entries[0], ix->d_entries[1]);
+        if (ix->usable && grid) sj_index_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, 1, d_cur[0], d_cur[1], d_cur[2], d_cur[3], ix->d_entries[0],
+                                                                     ix->d_entries[1], ix->d_entries[2], ix->d_entries[3], d_bad);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     } while (0);
-    dev_free(d_cur[0], s); dev_free(d_cur[1], s); dev_free(d_bad, s);
+    for (int t = 0; t < kSjTables; ++t) dev_free(d_cur[t], s);
+    dev_free(d_bad, s);
     if (e != cudaSuccess) { set_error("seed index: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     return MG_OK;
 }
@@ -270,108 +288,162 @@ __device__ __forceinline__ void sj_anchor(const GenomeView& gv, const QueriesVie
     atomicAdd(counts + (prm.strand > 0 ? id : (uint32_t)prm.N + id), 1u);
 }
 
-// every gRNA whose H1 (table 0) / H2 (table 1) equals `key`; cls 0 = gap-free half, 1 = deletion variant, 2 = insertion variant
-__device__ __forceinline__ void sj_probe(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
-                                         const SeedIndexView& ix, const SjText& T, uint32_t key, int cls, int k, uint32_t* __restrict__ counts) {
-#pragma unroll
-    for (int tbl = 0; tbl < 2; ++tbl) {
-        if (cls == 2 && (tbl == 0 ? k < 1 : k > 8)) continue;       // insertion at query position k (H1: 1..9) or 10 + k (H2: 10..18)
-        const uint32_t a = __ldg(ix.start[tbl] + key), b = __ldg(ix.start[tbl] + key + 1);
-        for (uint32_t i = a; i < b; ++i) {
-            const uint2 e = __ldg(ix.entries[tbl] + i);
-            const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, id = e.y >> 8;
-            if (tbl == 0) {
-                if (cls == 0) {
-                    sj_anchor(gv, qv, ctx, prm, T, 11, 2, 0, id, qlo, qhi, counts);     // H1 on the final diagonal: w = p
-                    sj_anchor(gv, qv, ctx, prm, T, 12, 3, 0, id, qlo, qhi, counts);     // H1 on w - 1: w = p + 1
-                    sj_anchor(gv, qv, ctx, prm, T, 10, 4, 0, id, qlo, qhi, counts);     // H1 on w + 1: w = p - 1
-                } else if (cls == 1) sj_anchor(gv, qv, ctx, prm, T, 12, 5, k, id, qlo, qhi, counts);
-                else sj_anchor(gv, qv, ctx, prm, T, 10, 6, k, id, qlo, qhi, counts);
-            } else {
-                if (cls == 0) sj_anchor(gv, qv, ctx, prm, T, 1, 1, 0, id, qlo, qhi, counts);          // H2 at p: w = p - 10
-                else if (cls == 1) sj_anchor(gv, qv, ctx, prm, T, 2, 7, 10 + k, id, qlo, qhi, counts); // w - 1 = p - 10
-                else sj_anchor(gv, qv, ctx, prm, T, 0, 8, 10 + k, id, qlo, qhi, counts);               // w + 1 = p - 10
-            }
-        }
-    }
-}
-
-// Variant table (the same for every text position): [19:0] substitution mask on the 20-bit key, [21:20] class
-// (0 gap-free half, 1 deletion, 2 insertion), [25:22] k, [27:26] inserted base.  One loop, one probe site: the 32 lanes of a
-// warp work on the same variant of 32 different text positions.
+// Variant table (the same for every text position): [19:0] substitution mask on the key, [21:20] class (0: the 10-mer at p and
+// its Hamming neighbours -> tables 0 / 1; 1: the 11-mer at p without its base k, substituted -> tables 0 / 1; 2: the 9-mer at
+// p, substituted -> tables 2 / 3), [25:22] k.  One loop: the 32 lanes of a warp work on the same variant of 32 text positions.
 static std::vector<uint32_t> sj_variants(int t, int g) {
     std::vector<uint32_t> v;
-    auto push = [&](uint32_t mask, uint32_t cls, uint32_t k, uint32_t x) { v.push_back(mask | (cls << 20) | (k << 22) | (x << 26)); };
-    push(0, 0, 0, 0);
+    auto push = [&](uint32_t mask, uint32_t cls, uint32_t k) { v.push_back(mask | (cls << 20) | (k << 22)); };
+    push(0, 0, 0);
     if (t >= 1)
         for (int i = 0; i < 10; ++i)
             for (uint32_t x = 1; x <= 3; ++x) {
-                push(x << (2 * i), 0, 0, 0);
+                push(x << (2 * i), 0, 0);
                 if (t >= 2)
                     for (int j = i + 1; j < 10; ++j)
-                        for (uint32_t y = 1; y <= 3; ++y) push((x << (2 * i)) | (y << (2 * j)), 0, 0, 0);
+                        for (uint32_t y = 1; y <= 3; ++y) push((x << (2 * i)) | (y << (2 * j)), 0, 0);
             }
     if (g < 0) return v;
     for (uint32_t k = 1; k <= 9; ++k) {                     // deletion: the 11-mer at p without its base k
-        push(0, 1, k, 0);
+        push(0, 1, k);
         if (g >= 1)
             for (int s = 0; s < 10; ++s)
-                for (uint32_t x = 1; x <= 3; ++x) push(x << (2 * s), 1, k, 0);
+                for (uint32_t x = 1; x <= 3; ++x) push(x << (2 * s), 1, k);
     }
-    for (uint32_t k = 0; k <= 9; ++k)                        // insertion: the 9-mer at p with base x inserted at k
-        for (uint32_t x = 0; x <= 3; ++x) {
-            push(0, 2, k, x);
-            if (g >= 1)
-                for (int s = 0; s < 10; ++s) {
-                    if (s == (int)k) continue;               // a substitution never touches the inserted base
-                    for (uint32_t y = 1; y <= 3; ++y) push(y << (2 * s), 2, k, x);
-                }
-        }
+    push(0, 2, 0);                                           // insertion: the 9-mer at p (the index knows which base was left out)
+    if (g >= 1)
+        for (int s = 0; s < 9; ++s)
+            for (uint32_t x = 1; x <= 3; ++x) push(x << (2 * s), 2, 0);
     return v;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kSjWarps = 8;                                  // warps per CTA
+constexpr int kSjQueue = 256;                                // candidate records per warp (8 B each)
+constexpr int kSjRound = 4;                                  // records a lane may append per round
+
+// The candidate records of a warp are evaluated 32 at a time, one per lane, whatever lane found them: the buckets of the 32
+// text positions of a warp hold 0, 1, 2 ... entries, and evaluating them where they were found would leave most lanes idle.
+// record: x = entry index, y = [1:0] table, [3:2] class, [7:4] k (deletion variants), [12:8] lane that owns the text context
+__device__ __forceinline__ void sj_evaluate(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
+                                            const SeedIndexView& ix, const SjText* texts, int64_t p_warp, uint2 rec,
+                                            uint32_t* __restrict__ counts) {
+    const int tbl = (int)(rec.y & 3u), cls = (int)((rec.y >> 2) & 3u), kv = (int)((rec.y >> 4) & 15u), src = (int)((rec.y >> 8) & 31u);
+    const uint2 e = __ldg(ix.entries[tbl] + rec.x);
+    const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, id = e.y >> 12;
+    const int ke = (int)((e.y >> 8) & 15u);                  // tables 2 / 3: the query position that has no partner in the text
+    SjText T = texts[src];
+    T.p = p_warp + src;
+    if (tbl == 0) {
+        if (cls == 0) {
+            sj_anchor(gv, qv, ctx, prm, T, 11, 2, 0, id, qlo, qhi, counts);     // H1 on the final diagonal: w = p
+            sj_anchor(gv, qv, ctx, prm, T, 12, 3, 0, id, qlo, qhi, counts);     // H1 on w - 1: w = p + 1
+            sj_anchor(gv, qv, ctx, prm, T, 10, 4, 0, id, qlo, qhi, counts);     // H1 on w + 1: w = p - 1
+        } else sj_anchor(gv, qv, ctx, prm, T, 12, 5, kv, id, qlo, qhi, counts);                       // deletion before query position k
+    } else if (tbl == 1) {
+        if (cls == 0) sj_anchor(gv, qv, ctx, prm, T, 1, 1, 0, id, qlo, qhi, counts);                  // H2 at p: w = p - 10
+        else sj_anchor(gv, qv, ctx, prm, T, 2, 7, 10 + kv, id, qlo, qhi, counts);                      // w - 1 = p - 10
+    } else if (tbl == 2) sj_anchor(gv, qv, ctx, prm, T, 10, 6, ke, id, qlo, qhi, counts);             // insertion at query position ke (1..9)
+    else sj_anchor(gv, qv, ctx, prm, T, 0, 8, 10 + ke, id, qlo, qhi, counts);                          // insertion at 10..18: w + 1 = p - 10
+}
+
+__global__ void __launch_bounds__(32 * kSjWarps)
 sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx* __restrict__ ctx, SjParams prm,
                const uint32_t* __restrict__ variants, int n_variants, int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts) {
-    const int64_t p = p_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= p_end) return;
+    __shared__ SjText s_text[kSjWarps][32];
+    __shared__ uint2 s_queue[kSjWarps][kSjQueue];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p_warp = p_begin + ((int64_t)blockIdx.x * kSjWarps + warp) * 32;
+    const int64_t p = p_warp + lane;
     SjText T;
     T.p = p;
     T.okmask = 0u;
     T.nearmask = 0u;
-    for (int wi = 0; wi <= 12; ++wi) {
-        const int64_t wf = sj_fwd_window(gv, prm.strand, p - 11 + wi);
-        if (wf < prm.wb || wf >= prm.we || sj_dirty(gv, wf)) continue;
-        T.okmask |= 1u << wi;
-        if (gv.n_masks && sj_mask_near(gv, wf - 3, wf + 24)) T.nearmask |= 1u << wi;
+    T.tlo0 = T.tlo1 = T.thi0 = T.thi1 = 0u;
+    uint32_t T10 = 0u, U11 = 0u, S9 = 0u;
+    if (p < p_end) {
+        for (int wi = 0; wi <= 12; ++wi) {
+            const int64_t wf = sj_fwd_window(gv, prm.strand, p - 11 + wi);
+            if (wf < prm.wb || wf >= prm.we || sj_dirty(gv, wf)) continue;
+            T.okmask |= 1u << wi;
+            if (gv.n_masks && sj_mask_near(gv, wf - 3, wf + 24)) T.nearmask |= 1u << wi;
+        }
     }
-    if (T.okmask == 0u) return;
-    uint32_t lo0, hi0, lo1, hi1;
-    sj_load32(gv, prm.strand, p - 12, lo0, hi0);
-    sj_load32(gv, prm.strand, p + 20, lo1, hi1);
-    T.tlo0 = compress_even(lo0, hi0); T.thi0 = compress_even(lo0 >> 1, hi0 >> 1);
-    T.tlo1 = compress_even(lo1, hi1); T.thi1 = compress_even(lo1 >> 1, hi1 >> 1);
-    const unsigned long long W = (((unsigned long long)hi0 << 32) | lo0) >> 24;       // 2-bit codes from base p on (20 bases)
-    const uint32_t T10 = (uint32_t)W & kFull, U11 = (uint32_t)W & 0x3FFFFFu, S9 = (uint32_t)W & 0x3FFFFu;
+    if (!__any_sync(0xFFFFFFFFu, T.okmask != 0u)) return;          // the whole warp sits in padding / outside the shard
+    if (T.okmask) {
+        uint32_t lo0, hi0, lo1, hi1;
+        sj_load32(gv, prm.strand, p - 12, lo0, hi0);
+        sj_load32(gv, prm.strand, p + 20, lo1, hi1);
+        T.tlo0 = compress_even(lo0, hi0); T.thi0 = compress_even(lo0 >> 1, hi0 >> 1);
+        T.tlo1 = compress_even(lo1, hi1); T.thi1 = compress_even(lo1 >> 1, hi1 >> 1);
+        const unsigned long long W = (((unsigned long long)hi0 << 32) | lo0) >> 24;   // 2-bit codes from base p on (20 bases)
+        T10 = (uint32_t)W & kFull; U11 = (uint32_t)W & 0x3FFFFFu; S9 = (uint32_t)W & 0x3FFFFu;
+    }
+    s_text[warp][lane] = T;
+    __syncwarp();
+    const bool live = T.okmask != 0u;
+    uint2* const queue = s_queue[warp];
+    int qlen = 0;                                                   // warp-uniform
 
-    for (int v = 0; v < n_variants; ++v) {
+    auto drain = [&](bool all) {
+        while (qlen >= 32 || (all && qlen > 0)) {
+            const int take = qlen < 32 ? qlen : 32;
+            __syncwarp();
+            if (lane < take) sj_evaluate(gv, qv, ctx, prm, ix, s_text[warp], p_warp, queue[qlen - take + lane], counts);
+            qlen -= take;
+            __syncwarp();
+        }
+    };
+
+    // keys and bucket bounds of variant v for this lane: tables ta / ta + 1
+    auto bounds = [&](int v, uint32_t& meta, uint32_t& a0, uint32_t& b0, uint32_t& a1, uint32_t& b1) {
         const uint32_t d = __ldg(variants + v);
         const uint32_t mask = d & kFull;
         const int cls = (int)((d >> 20) & 3u), k = (int)((d >> 22) & 15u);
-        uint32_t key;
-        if (cls == 0) {
-            key = T10 ^ mask;
-        } else if (cls == 1) {
+        uint32_t key = T10 ^ mask;
+        bool valid = live;
+        int ta = 0;
+        if (cls == 1) {
             // two equal neighbours give the same string whichever is removed: the first one (smaller k) stands for both
-            if (((U11 >> (2 * k)) & 3u) == ((U11 >> (2 * k - 2)) & 3u)) continue;
+            valid = valid && ((U11 >> (2 * k)) & 3u) != ((U11 >> (2 * k - 2)) & 3u);
             const uint32_t low = (1u << (2 * k)) - 1u;
             key = ((U11 & low) | ((U11 >> (2 * k + 2)) << (2 * k))) ^ mask;
-        } else {
-            const uint32_t low = (1u << (2 * k)) - 1u, x = (d >> 26) & 3u;
-            key = ((S9 & low) | (x << (2 * k)) | ((S9 >> (2 * k)) << (2 * k + 2))) ^ mask;
+        } else if (cls == 2) {
+            key = S9 ^ mask;
+            ta = 2;
         }
-        sj_probe(gv, qv, ctx, prm, ix, T, key, cls, k, counts);
+        meta = (uint32_t)ta | ((uint32_t)cls << 2) | ((uint32_t)k << 4) | ((uint32_t)lane << 8);
+        a0 = b0 = a1 = b1 = 0u;
+        if (valid) {
+            a0 = __ldg(ix.start[ta] + key); b0 = __ldg(ix.start[ta] + key + 1);
+            a1 = __ldg(ix.start[ta + 1] + key); b1 = __ldg(ix.start[ta + 1] + key + 1);
+        }
+    };
+
+    uint32_t meta, a0, b0, a1, b1;
+    bounds(0, meta, a0, b0, a1, b1);
+    for (int v = 0; v < n_variants; ++v) {
+        uint32_t nmeta = 0u, na0 = 0u, nb0 = 0u, na1 = 0u, nb1 = 0u;
+        if (v + 1 < n_variants) bounds(v + 1, nmeta, na0, nb0, na1, nb1);    // the next variant's loads are in flight while this one is queued
+        while (__any_sync(0xFFFFFFFFu, a0 < b0 || a1 < b1)) {
+            if (qlen > kSjQueue - 32 * kSjRound) drain(false);
+            // every lane appends up to kSjRound records (table ta first)
+            const int have = (int)min((uint32_t)kSjRound, (b0 - a0) + (b1 - a1));
+            int off = have;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, off, d); if (lane >= d) off += o; }
+            const int total = __shfl_sync(0xFFFFFFFFu, off, 31);
+            off -= have;
+            for (int j = 0; j < have; ++j) {
+                uint2 rec;
+                if (a0 < b0) { rec.x = a0++; rec.y = meta; } else { rec.x = a1++; rec.y = meta + 1u; }
+                queue[qlen + off + j] = rec;
+            }
+            qlen += total;
+            drain(false);
+        }
+        meta = nmeta; a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
     }
+    drain(true);
 }
 
 // 32-base blocks of [b0, b1) that hold an invalid base
@@ -388,7 +460,7 @@ __global__ void sj_dirty_blocks_kernel(GenomeView gv, int64_t b0, int64_t b1, un
 // Can this screen use the seed-and-join path?  (criterion class, gRNA length, set size; MG_GAPPED=dp|seedjoin overrides the size rule)
 bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
     if (crit->n_units != 0 || crit->max_gap != 1 || !crit->pamless || q->len != kSjL) return false;
-    if (crit->max_mismatch < 0 || crit->max_mismatch > 4 || q->n < 1 || q->n >= (1 << 24)) return false;
+    if (crit->max_mismatch < 0 || crit->max_mismatch > 4 || q->n < 1 || q->n > (1 << 20)) return false;    // 20-bit gRNA index in an entry
     const char* env = getenv("MG_GAPPED");
     if (env && strcmp(env, "dp") == 0) return false;
     if (env && strcmp(env, "seedjoin") == 0) return true;
@@ -449,7 +521,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     prm.N = q->n; prm.M = crit->max_mismatch; prm.t = (prm.M + 1) / 2; prm.g = prm.M - prm.t - 1;
     prm.wb = wb; prm.we = we;
     SeedIndexView iv;
-    for (int t = 0; t < 2; ++t) { iv.start[t] = ix->d_start[t]; iv.entries[t] = ix->d_entries[t]; }
+    for (int t = 0; t < kSjTables; ++t) { iv.start[t] = ix->d_start[t]; iv.entries[t] = ix->d_entries[t]; }
     const std::vector<uint32_t> vars = sj_variants(prm.t, prm.g);
     uint32_t* d_vars = nullptr;
     MG_CUDA(dev_alloc((void**)&d_vars, sizeof(uint32_t) * vars.size(), s));
@@ -462,7 +534,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
-        sj_scan_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, s>>>(gv, q->view(), iv, d_ctx, prm, d_vars, (int)vars.size(), p0, p1, d_counts);
+        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, q->view(), iv, d_ctx, prm, d_vars, (int)vars.size(), p0, p1, d_counts);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
