@@ -169,10 +169,10 @@ struct SjParams {
     int64_t wb, we;            // forward window starts owned by this call
 };
 
-struct SjText {
+struct alignas(16) SjText {
     uint32_t tlo0, tlo1, thi0, thi1;   // bit planes of the 64 strand bases from p - 12 (bit i of word 0 = base p - 12 + i)
     uint32_t okmask, nearmask;         // per candidate window wi = 0..12 (w = p - 11 + wi): owned and clean / a mask is near
-    int64_t p;
+    uint32_t pad0, pad1;
 };
 
 // 32 bases of the strand's text from strand position x0, as 2-bit codes (base i at bits 2i of hi:lo)
@@ -254,35 +254,42 @@ __device__ __noinline__ int sj_first_applicable(uint32_t D0, uint32_t DM, uint32
     return 0;
 }
 
-// One candidate (gRNA id, query planes) reached through route r (k_probe: gap position in query coordinates for r >= 5)
-// at candidate window wi: count the anchor if it is problematic and this (route, k) owns it.
-__device__ __forceinline__ void sj_anchor(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
-                                          const SjText& T, int wi, int r, int k_probe, uint32_t id, uint32_t qlo, uint32_t qhi,
-                                          uint32_t* __restrict__ counts) {
-    if (!((T.okmask >> wi) & 1u)) return;
-    const int o = wi + 1, M = prm.M, t = prm.t;
-    const bool near = (T.nearmask >> wi) & 1u;
+// One candidate (gRNA planes) reached through route r (k_probe: gap position in query coordinates for r >= 5) at candidate
+// window wi.  Stage 1: cheap NECESSARY conditions for "the anchor is problematic and its canonical alignment implies route r
+// (and k_probe)"; a few per cent pass.  An insertion skips one query position, so bounds that use "mismatches on both
+// diagonals" get one unit of slack.  Near a mask the exact verifier decides, so everything passes.
+__device__ __forceinline__ bool sj_stage1(const SjParams& prm, const SjText& T, int wi, int r, int k_probe, uint32_t qlo, uint32_t qhi) {
+    if (!((T.okmask >> wi) & 1u)) return false;
+    if ((T.nearmask >> wi) & 1u) return true;
+    const int o = wi + 1, M = prm.M;
     const uint32_t D0 = sj_diag(T, qlo, qhi, o);
-    // Necessary conditions for "the canonical alignment of a problematic anchor implies route r" (cheap; a few per cent pass).
-    // An insertion skips one query position, so bounds that use "mismatches on both diagonals" get one unit of slack.
-    if (!near) {
-        if (r == 2 && __popc(D0) > M + 1) return;                              // R2 only owns ungapped alignments
-        if ((r == 5 || r == 6) && __popc(D0 & kH2M) > M) return;              // H2 is gap-free on the final diagonal
-    }
-    const uint32_t DM = sj_diag(T, qlo, qhi, o - 1), DP = sj_diag(T, qlo, qhi, o + 1);
-    const int64_t w = T.p - 11 + wi;                  // strand window start of the final diagonal
+    if (r == 2) return __popc(D0) <= M + 1;                                    // R2 only owns ungapped alignments
+    const uint32_t lowk = (1u << k_probe) - 1u;
+    if (r == 5 || r == 7) return __popc(sj_diag(T, qlo, qhi, o - 1) & lowk) + __popc(D0 & ~lowk) <= M;          // the deletion before k fits
+    if (r == 6 || r == 8) return __popc(sj_diag(T, qlo, qhi, o + 1) & lowk) + __popc(D0 & ~(2u * lowk + 1u)) <= M;   // the insertion at k fits
+    if (r == 3) { const uint32_t DM = sj_diag(T, qlo, qhi, o - 1); return __popc(DM & kH1M) + __popc(DM & D0 & kH2M) <= M; }
+    if (r == 4) { const uint32_t DP = sj_diag(T, qlo, qhi, o + 1); return __popc(DP & kH1M) + __popc(DP & D0 & kH2M) <= M + 1; }
+    const uint32_t DM = sj_diag(T, qlo, qhi, o - 1), DP = sj_diag(T, qlo, qhi, o + 1);                           // r == 1
+    return min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1;
+}
+
+// Stage 2 (survivors of stage 1, again 32 at a time): the exact decision and the ownership rule.
+// record: x, y = index entry; z = [3:0] wi, [7:4] route, [12:8] k_probe, [17:13] lane that owns the text context
+__device__ __noinline__ void sj_stage2(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
+                                       const SjText* texts, int64_t p_warp, const uint4 rec, uint32_t* __restrict__ counts) {
+    const int wi = (int)(rec.z & 15u), r = (int)((rec.z >> 4) & 15u), k_probe = (int)((rec.z >> 8) & 31u), src = (int)((rec.z >> 13) & 31u);
+    const uint32_t qlo = rec.x & kFull, qhi = ((rec.x >> 20) | (rec.y << 12)) & kFull, id = rec.y >> 12;
+    const SjText T = texts[src];
+    const int o = wi + 1;
+    const uint32_t D0 = sj_diag(T, qlo, qhi, o), DM = sj_diag(T, qlo, qhi, o - 1), DP = sj_diag(T, qlo, qhi, o + 1);
     int kq = 0;
-    if (near) {
-        const int owner = sj_first_applicable(D0, DM, DP, t, prm.g, kq);
+    if ((T.nearmask >> wi) & 1u) {
+        const int owner = sj_first_applicable(D0, DM, DP, prm.t, prm.g, kq);
         if (owner != r || (r >= 5 && kq != k_probe)) return;
+        const int64_t w = p_warp + src - 11 + wi;     // strand window start of the final diagonal
         if (!verify_anchor(gv, *ctx, qv.codes + (size_t)id * kSjL, qv.packed + id, prm.strand, w + kSjL)) return;
     } else {
-        if (r == 1) { if (min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) > M + 1) return; }
-        else if (r == 3) { if (__popc(DM & kH1M) + __popc(DM & D0 & kH2M) > M) return; }
-        else if (r == 4) { if (__popc(DP & kH1M) + __popc(DP & D0 & kH2M) > M + 1) return; }
-        else if (r == 7) { if (__popc(DM & kH1M) > M) return; }
-        else if (r == 8) { if (__popc(DP & kH1M) > M) return; }
-        const int owner = sj_canonical(D0, DM, DP, M, t, kq);
+        const int owner = sj_canonical(D0, DM, DP, prm.M, prm.t, kq);
         if (owner != r || (r >= 5 && kq != k_probe)) return;
     }
     atomicAdd(counts + (prm.strand > 0 ? id : (uint32_t)prm.N + id), 1u);
@@ -318,47 +325,34 @@ static std::vector<uint32_t> sj_variants(int t, int g) {
 }
 
 constexpr int kSjWarps = 8;                                  // warps per CTA
-constexpr int kSjQueue = 256;                                // candidate records per warp (8 B each)
+constexpr int kSjQueue = 192;                                // candidate records per warp and queue (16 B each)
 constexpr int kSjRound = 4;                                  // records a lane may append per round
 
 // The candidate records of a warp are evaluated 32 at a time, one per lane, whatever lane found them: the buckets of the 32
 // text positions of a warp hold 0, 1, 2 ... entries, and evaluating them where they were found would leave most lanes idle.
-// record: x = entry index, y = [1:0] table, [3:2] class, [7:4] k (deletion variants), [12:8] lane that owns the text context
-__device__ __forceinline__ void sj_evaluate(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
-                                            const SeedIndexView& ix, const SjText* texts, int64_t p_warp, uint2 rec,
-                                            uint32_t* __restrict__ counts) {
-    const int tbl = (int)(rec.y & 3u), cls = (int)((rec.y >> 2) & 3u), kv = (int)((rec.y >> 4) & 15u), src = (int)((rec.y >> 8) & 31u);
-    const uint2 e = __ldg(ix.entries[tbl] + rec.x);
-    const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, id = e.y >> 12;
-    const int ke = (int)((e.y >> 8) & 15u);                  // tables 2 / 3: the query position that has no partner in the text
-    SjText T = texts[src];
-    T.p = p_warp + src;
-    if (tbl == 0) {
-        if (cls == 0) {
-            sj_anchor(gv, qv, ctx, prm, T, 11, 2, 0, id, qlo, qhi, counts);     // H1 on the final diagonal: w = p
-            sj_anchor(gv, qv, ctx, prm, T, 12, 3, 0, id, qlo, qhi, counts);     // H1 on w - 1: w = p + 1
-            sj_anchor(gv, qv, ctx, prm, T, 10, 4, 0, id, qlo, qhi, counts);     // H1 on w + 1: w = p - 1
-        } else sj_anchor(gv, qv, ctx, prm, T, 12, 5, kv, id, qlo, qhi, counts);                       // deletion before query position k
-    } else if (tbl == 1) {
-        if (cls == 0) sj_anchor(gv, qv, ctx, prm, T, 1, 1, 0, id, qlo, qhi, counts);                  // H2 at p: w = p - 10
-        else sj_anchor(gv, qv, ctx, prm, T, 2, 7, 10 + kv, id, qlo, qhi, counts);                      // w - 1 = p - 10
-    } else if (tbl == 2) sj_anchor(gv, qv, ctx, prm, T, 10, 6, ke, id, qlo, qhi, counts);             // insertion at query position ke (1..9)
-    else sj_anchor(gv, qv, ctx, prm, T, 0, 8, 10 + ke, id, qlo, qhi, counts);                          // insertion at 10..18: w + 1 = p - 10
-}
+// There is one queue per table of the current variant class, so the 32 candidates of a batch take the SAME route (no
+// divergence over the eight routes), and a record carries the index entry itself (loaded by the lane that found it, while the
+// records are being queued), so a batch never waits for memory.  The few per cent that pass stage 1 go to a third queue and
+// are decided 32 at a time as well (the exact evaluation is ~10x the work of stage 1).
+// candidate record: x, y = index entry; z = [3:0] k of a deletion variant, [8:4] lane that owns the text context
+constexpr int kSjSurvivors = 64;
+constexpr size_t kSjSmem = sizeof(uint4) * kSjWarps * (2 * kSjQueue + kSjSurvivors) + sizeof(SjText) * kSjWarps * 32;
 
-__global__ void __launch_bounds__(32 * kSjWarps)
+__global__ void __launch_bounds__(32 * kSjWarps, 2)
 sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx* __restrict__ ctx, SjParams prm,
                const uint32_t* __restrict__ variants, int n_variants, int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts) {
-    __shared__ SjText s_text[kSjWarps][32];
-    __shared__ uint2 s_queue[kSjWarps][kSjQueue];
+    extern __shared__ uint4 sj_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* q0 = sj_smem + (size_t)warp * (2 * kSjQueue + kSjSurvivors);      // this warp's queues
+    uint4* q1 = q0 + kSjQueue;
+    uint4* qs = q1 + kSjQueue;
+    SjText* texts = reinterpret_cast<SjText*>(sj_smem + (size_t)kSjWarps * (2 * kSjQueue + kSjSurvivors)) + warp * 32;
     const int64_t p_warp = p_begin + ((int64_t)blockIdx.x * kSjWarps + warp) * 32;
     const int64_t p = p_warp + lane;
     SjText T;
-    T.p = p;
     T.okmask = 0u;
     T.nearmask = 0u;
-    T.tlo0 = T.tlo1 = T.thi0 = T.thi1 = 0u;
+    T.tlo0 = T.tlo1 = T.thi0 = T.thi1 = T.pad0 = T.pad1 = 0u;
     uint32_t T10 = 0u, U11 = 0u, S9 = 0u;
     if (p < p_end) {
         for (int wi = 0; wi <= 12; ++wi) {
@@ -378,30 +372,63 @@ sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx
         const unsigned long long W = (((unsigned long long)hi0 << 32) | lo0) >> 24;   // 2-bit codes from base p on (20 bases)
         T10 = (uint32_t)W & kFull; U11 = (uint32_t)W & 0x3FFFFFu; S9 = (uint32_t)W & 0x3FFFFu;
     }
-    s_text[warp][lane] = T;
+    texts[lane] = T;
     __syncwarp();
     const bool live = T.okmask != 0u;
-    uint2* const queue = s_queue[warp];
-    int qlen = 0;                                                   // warp-uniform
+    int qlen0 = 0, qlen1 = 0, n_surv = 0;                           // warp-uniform
+    int cur_cls = 0;                                                // class of the records in the queues
 
-    auto drain = [&](bool all) {
+    // stage 1 of one anchor for the 32 candidates of a batch; survivors are compacted into the third queue
+    auto anchor = [&](bool act, const SjText& Tc, const uint4& rec, uint32_t qlo, uint32_t qhi, int src, int wi, int r, int kp) {
+        const bool pass = act && sj_stage1(prm, Tc, wi, r, kp, qlo, qhi);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+        if (m == 0u) return;
+        if (pass) qs[n_surv + __popc(m & ((1u << lane) - 1u))] = make_uint4(rec.x, rec.y, (uint32_t)wi | ((uint32_t)r << 4) | ((uint32_t)kp << 8) | ((uint32_t)src << 13), 0u);
+        n_surv += __popc(m);
+        if (n_surv >= 32) {
+            __syncwarp();
+            sj_stage2(gv, qv, ctx, prm, texts, p_warp, qs[n_surv - 32 + lane], counts);
+            n_surv -= 32;
+            __syncwarp();
+        }
+    };
+
+    // evaluate the records of queue j (tables of the current class), 32 at a time (all of them if `all`)
+    auto drain = [&](int j, bool all) {
+        int& qlen = j ? qlen1 : qlen0;
+        const uint4* queue = j ? q1 : q0;
         while (qlen >= 32 || (all && qlen > 0)) {
             const int take = qlen < 32 ? qlen : 32;
             __syncwarp();
-            if (lane < take) sj_evaluate(gv, qv, ctx, prm, ix, s_text[warp], p_warp, queue[qlen - take + lane], counts);
+            const bool act = lane < take;
+            const uint4 rec = act ? queue[qlen - take + lane] : make_uint4(0u, 0u, 0u, 0u);
+            const int kv = (int)(rec.z & 15u), src = (int)((rec.z >> 4) & 31u);
+            const uint32_t qlo = rec.x & kFull, qhi = ((rec.x >> 20) | (rec.y << 12)) & kFull;
+            const int ke = (int)((rec.y >> 8) & 15u);               // tables 2 / 3: the position of the half that has no partner in the text
+            const SjText Tc = texts[src];
+            if (cur_cls == 0 && j == 0) {
+                anchor(act, Tc, rec, qlo, qhi, src, 11, 2, 0);      // H1 on the final diagonal: w = p
+                anchor(act, Tc, rec, qlo, qhi, src, 12, 3, 0);      // H1 on w - 1: w = p + 1
+                anchor(act, Tc, rec, qlo, qhi, src, 10, 4, 0);      // H1 on w + 1: w = p - 1
+            } else if (cur_cls == 0) anchor(act, Tc, rec, qlo, qhi, src, 1, 1, 0);              // H2 at p: w = p - 10
+            else if (cur_cls == 1 && j == 0) anchor(act, Tc, rec, qlo, qhi, src, 12, 5, kv);    // deletion before query position k
+            else if (cur_cls == 1) anchor(act, Tc, rec, qlo, qhi, src, 2, 7, 10 + kv);          // w - 1 = p - 10
+            else if (j == 0) anchor(act, Tc, rec, qlo, qhi, src, 10, 6, ke);                    // insertion at query position ke (1..9)
+            else anchor(act, Tc, rec, qlo, qhi, src, 0, 8, 10 + ke);                            // insertion at 10..18: w + 1 = p - 10
             qlen -= take;
             __syncwarp();
         }
     };
 
-    // keys and bucket bounds of variant v for this lane: tables ta / ta + 1
-    auto bounds = [&](int v, uint32_t& meta, uint32_t& a0, uint32_t& b0, uint32_t& a1, uint32_t& b1) {
+    // key and bucket bounds of variant v for this lane in tables ta / ta + 1
+    auto bounds = [&](int v, int& cls, int& ta, uint32_t& tag, uint32_t& a0, uint32_t& b0, uint32_t& a1, uint32_t& b1) {
         const uint32_t d = __ldg(variants + v);
         const uint32_t mask = d & kFull;
-        const int cls = (int)((d >> 20) & 3u), k = (int)((d >> 22) & 15u);
+        const int k = (int)((d >> 22) & 15u);
+        cls = (int)((d >> 20) & 3u);
         uint32_t key = T10 ^ mask;
         bool valid = live;
-        int ta = 0;
+        ta = 0;
         if (cls == 1) {
             // two equal neighbours give the same string whichever is removed: the first one (smaller k) stands for both
             valid = valid && ((U11 >> (2 * k)) & 3u) != ((U11 >> (2 * k - 2)) & 3u);
@@ -411,7 +438,7 @@ sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx
             key = S9 ^ mask;
             ta = 2;
         }
-        meta = (uint32_t)ta | ((uint32_t)cls << 2) | ((uint32_t)k << 4) | ((uint32_t)lane << 8);
+        tag = (uint32_t)k | ((uint32_t)lane << 4);
         a0 = b0 = a1 = b1 = 0u;
         if (valid) {
             a0 = __ldg(ix.start[ta] + key); b0 = __ldg(ix.start[ta] + key + 1);
@@ -419,31 +446,46 @@ sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx
         }
     };
 
-    uint32_t meta, a0, b0, a1, b1;
-    bounds(0, meta, a0, b0, a1, b1);
+    int cls, ta;
+    uint32_t tag, a0, b0, a1, b1;
+    bounds(0, cls, ta, tag, a0, b0, a1, b1);
     for (int v = 0; v < n_variants; ++v) {
-        uint32_t nmeta = 0u, na0 = 0u, nb0 = 0u, na1 = 0u, nb1 = 0u;
-        if (v + 1 < n_variants) bounds(v + 1, nmeta, na0, nb0, na1, nb1);    // the next variant's loads are in flight while this one is queued
+        int ncls = 0, nta = 0;
+        uint32_t ntag = 0u, na0 = 0u, nb0 = 0u, na1 = 0u, nb1 = 0u;
+        if (v + 1 < n_variants) bounds(v + 1, ncls, nta, ntag, na0, nb0, na1, nb1);   // the next variant's loads are in flight meanwhile
+        if (cls != cur_cls) { drain(0, true); drain(1, true); cur_cls = cls; }         // a queue only ever holds one route family
         while (__any_sync(0xFFFFFFFFu, a0 < b0 || a1 < b1)) {
-            if (qlen > kSjQueue - 32 * kSjRound) drain(false);
-            // every lane appends up to kSjRound records (table ta first)
-            const int have = (int)min((uint32_t)kSjRound, (b0 - a0) + (b1 - a1));
-            int off = have;
+            // every lane appends up to kSjRound records per table; one scan for both counts (16 bits each)
+            const int h0 = (int)min((uint32_t)kSjRound, b0 - a0), h1 = (int)min((uint32_t)kSjRound, b1 - a1);
+            int off = h0 | (h1 << 16);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, off, d); if (lane >= d) off += o; }
             const int total = __shfl_sync(0xFFFFFFFFu, off, 31);
-            off -= have;
-            for (int j = 0; j < have; ++j) {
-                uint2 rec;
-                if (a0 < b0) { rec.x = a0++; rec.y = meta; } else { rec.x = a1++; rec.y = meta + 1u; }
-                queue[qlen + off + j] = rec;
+            off -= h0 | (h1 << 16);
+            const int o0 = qlen0 + (off & 0xFFFF), o1 = qlen1 + (off >> 16);
+            uint2 e0[kSjRound], e1[kSjRound];
+#pragma unroll
+            for (int j = 0; j < kSjRound; ++j) {                    // the entry loads of a round are in flight together
+                e0[j] = j < h0 ? __ldg(ix.entries[ta] + a0 + j) : make_uint2(0u, 0u);
+                e1[j] = j < h1 ? __ldg(ix.entries[ta + 1] + a1 + j) : make_uint2(0u, 0u);
             }
-            qlen += total;
-            drain(false);
+#pragma unroll
+            for (int j = 0; j < kSjRound; ++j) {
+                if (j < h0) q0[o0 + j] = make_uint4(e0[j].x, e0[j].y, tag, 0u);
+                if (j < h1) q1[o1 + j] = make_uint4(e1[j].x, e1[j].y, tag, 0u);
+            }
+            a0 += h0; a1 += h1;
+            qlen0 += total & 0xFFFF;
+            qlen1 += total >> 16;
+            drain(0, false);
+            drain(1, false);
         }
-        meta = nmeta; a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
+        cls = ncls; ta = nta; tag = ntag; a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
     }
-    drain(true);
+    drain(0, true);
+    drain(1, true);
+    __syncwarp();
+    if (lane < n_surv) sj_stage2(gv, qv, ctx, prm, texts, p_warp, qs[lane], counts);
 }
 
 // 32-base blocks of [b0, b1) that hold an invalid base
@@ -528,13 +570,15 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     e = cudaMemcpyAsync(d_vars, vars.data(), sizeof(uint32_t) * vars.size(), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);              // vars lives on this stack frame
     if (e != cudaSuccess) { dev_free(d_vars, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
-    for (int z = 0; z < 2; ++z) {
+    const size_t smem = kSjSmem;
+    e = cudaFuncSetAttribute(sj_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int z = 0; z < 2 && e == cudaSuccess; ++z) {
         prm.strand = z == 0 ? 1 : -1;
         // strand windows of the owned forward windows, then the positions that can reach them (w - 1 .. w + 11)
         const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
-        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, q->view(), iv, d_ctx, prm, d_vars, (int)vars.size(), p0, p1, d_counts);
+        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, smem, s>>>(gv, q->view(), iv, d_ctx, prm, d_vars, (int)vars.size(), p0, p1, d_counts);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
