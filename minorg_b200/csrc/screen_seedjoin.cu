@@ -24,19 +24,18 @@
 // with ~25 instructions (three diagonal mismatch masks from bit planes held in registers, one route-specific necessary
 // test), and ~4 % of those with the exact evaluation above.
 //
-// Exactly-once counting.  An anchor can be reached through several routes and variants (from different threads).  Where no
-// mask is near, it is counted by the route that the CANONICAL alignment (ungapped if it fits, else the deletion with the
-// smallest k, else the insertion with the smallest k) implies: its gap-free half if that has <= t mismatches (H2 first),
-// else its gapped half with that k.  Where a masked (on-target) interval is near, "problematic" also depends on spans, so
-// the exact verifier of the DP path decides (verify_anchor) and the anchor belongs to the FIRST applicable route in the
-// order R1..R8 (smallest k inside a gapped route).  Both rules are functions of (gRNA, anchor) only, so every thread that
-// reaches the anchor agrees on who counts it.
+// Exactly-once counting.  An anchor can be reached through several routes and variants (from different threads).  It is
+// counted by the route that its CANONICAL alignment (ungapped if it fits, else the deletion with the smallest k, else the
+// insertion with the smallest k) implies: its gap-free half if that has <= t mismatches (H2 first), else its gapped half
+// with that k.  That is a function of (gRNA, anchor) only, so every thread that reaches the anchor agrees on who counts it.
 //
 // Dirty windows.  A window whose bases [w-3, w+23) touch a 32-base block with an invalid base (N, IUPAC, contig padding,
-// i.e. also everything that hangs off a contig end) is left to the DP path: the host collects those blocks, merges them
-// into window ranges and runs the prefilter + verifier on them.  Both paths use the same predicate, so every anchor is
-// owned by exactly one of them.
+// i.e. also everything that hangs off a contig end), or whose bases [w-3, w+24) meet a masked (on-target) interval - there
+// "problematic" also depends on spans - is left to the DP path and its exact verifier: the host collects those blocks and
+// the intervals, merges them into window ranges and runs the prefilter + verifier on them.  Both paths use the same
+// predicates, so every anchor is owned by exactly one of them.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -53,26 +52,38 @@ constexpr uint32_t kH1M = 0x3FFu, kH2M = 0xFFC00u, kFull = 0xFFFFFu;
 // an insertion in the gRNA is found by asking for the text's 9-mer instead of trying every inserted base at every position.
 // Entry (8 B): [19:0] low-bit plane of the 20 query bases, [39:20] high-bit plane, [43:40] k (position inside the half),
 // [63:44] gRNA index (< 2^20).
+// Directory: ONE 8-byte word per key for a pair of tables (the same key is always looked up in both), each half =
+// first entry << count bits | entry count; 12 count bits for tables 0 / 1, 8 for tables 2 / 3 (a gRNA set with a fuller
+// bucket - thousands of gRNA sharing a half - stays with the DP path).
 constexpr int kSjTables = 4;
 constexpr uint32_t kSjKeys9 = 1u << 18;
+constexpr int kSjCountBits01 = 12, kSjCountBits23 = 8;
 __host__ __device__ constexpr uint32_t sj_table_keys(int t) { return t < 2 ? kSjKeys : kSjKeys9; }
 
 struct SeedIndex {
-    uint32_t* d_start[kSjTables] = {nullptr, nullptr, nullptr, nullptr};   // [keys + 1] first entry of each key
-    uint2* d_entries[kSjTables] = {nullptr, nullptr, nullptr, nullptr};
+    uint2* d_dir01 = nullptr;                        // [4^10] directory of tables 0 / 1
+    uint2* d_dir23 = nullptr;                        // [4^9]  directory of tables 2 / 3
+    uint2* d_entries0 = nullptr;                     // [n]
+    uint2* d_entries1 = nullptr;                     // [n]
+    uint2* d_entries23 = nullptr;                    // [9n] table 2, then [9n] table 3
     int n = 0;
-    bool usable = false;                             // false: some gRNA has a non-ACGT base (the set stays with the DP path)
+    bool usable = false;                             // false: a gRNA with a non-ACGT base or an overfull bucket (the set stays with the DP path)
     cudaStream_t stream = nullptr;
 };
 
 struct SeedIndexView {
-    const uint32_t* start[kSjTables];
-    const uint2* entries[kSjTables];
+    const uint2* dir01;
+    const uint2* dir23;
+    const uint2* entries0;
+    const uint2* entries1;
+    const uint2* entries23;
+    uint32_t off3;                                   // first entry of table 3 in entries23
 };
 
 void seed_index_free(SeedIndex* ix) {
     if (!ix) return;
-    for (int h = 0; h < kSjTables; ++h) { dev_free(ix->d_start[h], ix->stream); dev_free(ix->d_entries[h], ix->stream); }
+    dev_free(ix->d_dir01, ix->stream); dev_free(ix->d_dir23, ix->stream);
+    dev_free(ix->d_entries0, ix->stream); dev_free(ix->d_entries1, ix->stream); dev_free(ix->d_entries23, ix->stream);
     delete ix;
 }
 
@@ -121,38 +132,52 @@ static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out
     *out = ix;
     uint32_t* d_cur[kSjTables] = {nullptr, nullptr, nullptr, nullptr};
     unsigned int* d_bad = nullptr;
-    std::vector<uint32_t> h((size_t)kSjKeys + 1);
+    std::vector<uint32_t> h((size_t)kSjKeys);
+    std::vector<uint2> dir((size_t)kSjKeys);
+    const size_t n1 = (size_t)std::max(1, q->n);
     cudaError_t e = cudaSuccess;
     do {
         for (int t = 0; t < kSjTables && e == cudaSuccess; ++t) {
-            const size_t kb = sizeof(uint32_t) * ((size_t)sj_table_keys(t) + 1);
-            e = dev_alloc((void**)&ix->d_start[t], kb, s);
-            if (e == cudaSuccess) e = dev_alloc((void**)&ix->d_entries[t], sizeof(uint2) * (size_t)std::max(1, q->n) * (t < 2 ? 1 : 9), s);
-            if (e == cudaSuccess) e = dev_alloc((void**)&d_cur[t], kb, s);
+            const size_t kb = sizeof(uint32_t) * (size_t)sj_table_keys(t);
+            e = dev_alloc((void**)&d_cur[t], kb, s);
             if (e == cudaSuccess) e = cudaMemsetAsync(d_cur[t], 0, kb, s);
         }
         if (e != cudaSuccess) break;
+        if ((e = dev_alloc((void**)&ix->d_dir01, sizeof(uint2) * kSjKeys, s)) != cudaSuccess) break;
+        if ((e = dev_alloc((void**)&ix->d_dir23, sizeof(uint2) * kSjKeys9, s)) != cudaSuccess) break;
+        if ((e = dev_alloc((void**)&ix->d_entries0, sizeof(uint2) * n1, s)) != cudaSuccess) break;
+        if ((e = dev_alloc((void**)&ix->d_entries1, sizeof(uint2) * n1, s)) != cudaSuccess) break;
+        if ((e = dev_alloc((void**)&ix->d_entries23, sizeof(uint2) * n1 * 18, s)) != cudaSuccess) break;
         if ((e = dev_alloc((void**)&d_bad, 4, s)) != cudaSuccess) break;
         if ((e = cudaMemsetAsync(d_bad, 0, 4, s)) != cudaSuccess) break;
         const int grid = (q->n + 255) / 256;
         if (grid) sj_index_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, 0, d_cur[0], d_cur[1], d_cur[2], d_cur[3], nullptr, nullptr, nullptr, nullptr, d_bad);
         unsigned int bad = 0;
         if ((e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        bool fits = true;
         for (int t = 0; t < kSjTables && e == cudaSuccess; ++t) {
             // exclusive scan on the host: <= 4 MB per table, once per gRNA set
-            const size_t nk = (size_t)sj_table_keys(t) + 1, kb = sizeof(uint32_t) * nk;
+            const size_t nk = (size_t)sj_table_keys(t), kb = sizeof(uint32_t) * nk;
+            const int bits = t < 2 ? kSjCountBits01 : kSjCountBits23;
             if ((e = cudaMemcpyAsync(h.data(), d_cur[t], kb, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
             uint32_t run = 0;
-            for (size_t k = 0; k < nk; ++k) { const uint32_t c = h[k]; h[k] = run; run += c; }
-            if ((e = cudaMemcpyAsync(ix->d_start[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+            for (size_t k = 0; k < nk; ++k) {
+                const uint32_t c = h[k];
+                if (c >= (1u << bits)) fits = false;
+                const uint32_t word = c ? (run << bits) | c : 0u;
+                if (t & 1) dir[k].y = word; else dir[k].x = word;
+                h[k] = run;
+                run += c;
+            }
             if ((e = cudaMemcpyAsync(d_cur[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
-            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+            if (t & 1) e = cudaMemcpyAsync(t == 1 ? ix->d_dir01 : ix->d_dir23, dir.data(), sizeof(uint2) * nk, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         }
         if (e != cudaSuccess) break;
-        ix->usable = bad == 0;
-        if (ix->usable && grid) sj_index_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, 1, d_cur[0], d_cur[1], d_cur[2], d_cur[3], ix->d_entries[0],
-                                                                     ix->d_entries[1], ix->d_entries[2], ix->d_entries[3], d_bad);
+        ix->usable = bad == 0 && fits;
+        if (ix->usable && grid) sj_index_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, 1, d_cur[0], d_cur[1], d_cur[2], d_cur[3], ix->d_entries0,
+                                                                     ix->d_entries1, ix->d_entries23, ix->d_entries23 + 9 * n1, d_bad);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     } while (0);
@@ -169,11 +194,19 @@ struct SjParams {
     int64_t wb, we;            // forward window starts owned by this call
 };
 
-struct alignas(16) SjText {
+struct SjText {                        // a text position's context, kept in its lane's registers
     uint32_t tlo0, tlo1, thi0, thi1;   // bit planes of the 64 strand bases from p - 12 (bit i of word 0 = base p - 12 + i)
-    uint32_t okmask, nearmask;         // per candidate window wi = 0..12 (w = p - 11 + wi): owned and clean / a mask is near
-    uint32_t pad0, pad1;
+    uint32_t okmask;                   // per candidate window wi = 0..12 (w = p - 11 + wi): owned by this call, clean and away from masks
 };
+
+// the context of lane src (any permutation of lanes; every lane of the warp must call)
+__device__ __forceinline__ SjText sj_text_from(const SjText& T, int src) {
+    SjText r;
+    r.tlo0 = __shfl_sync(0xFFFFFFFFu, T.tlo0, src); r.tlo1 = __shfl_sync(0xFFFFFFFFu, T.tlo1, src);
+    r.thi0 = __shfl_sync(0xFFFFFFFFu, T.thi0, src); r.thi1 = __shfl_sync(0xFFFFFFFFu, T.thi1, src);
+    r.okmask = __shfl_sync(0xFFFFFFFFu, T.okmask, src);
+    return r;
+}
 
 // 32 bases of the strand's text from strand position x0, as 2-bit codes (base i at bits 2i of hi:lo)
 __device__ __forceinline__ void sj_load32(const GenomeView& gv, int strand, int64_t x0, uint32_t& lo, uint32_t& hi) {
@@ -239,60 +272,20 @@ __device__ __noinline__ int sj_canonical(uint32_t D0, uint32_t DM, uint32_t DP, 
     return 0;
 }
 
-// First applicable route in the order R1..R8 (mask-near anchors), with the smallest k of a gapped route.
-__device__ __noinline__ int sj_first_applicable(uint32_t D0, uint32_t DM, uint32_t DP, int t, int g, int& kq) {
-    kq = 0;
-    if (__popc(D0 & kH2M) <= t) return 1;
-    if (__popc(D0 & kH1M) <= t) return 2;
-    if (__popc(DM & kH1M) <= t) return 3;
-    if (__popc(DP & kH1M) <= t) return 4;
-    if (g < 0) return 0;
-    for (int k = 1; k <= 9; ++k) { const uint32_t lowk = (1u << k) - 1u; if (__popc(DM & lowk) + __popc(D0 & kH1M & ~lowk) <= g) { kq = k; return 5; } }
-    for (int k = 1; k <= 9; ++k) { const uint32_t lowk = (1u << k) - 1u, lowk1 = (2u << k) - 1u; if (__popc(DP & lowk) + __popc(D0 & kH1M & ~lowk1) <= g) { kq = k; return 6; } }
-    for (int k = 11; k <= 19; ++k) { const uint32_t lowk = (1u << k) - 1u; if (__popc(DM & kH2M & lowk) + __popc(D0 & kFull & ~lowk) <= g) { kq = k; return 7; } }
-    for (int k = 10; k <= 18; ++k) { const uint32_t lowk = (1u << k) - 1u, lowk1 = (2u << k) - 1u; if (__popc(DP & kH2M & lowk) + __popc(D0 & kFull & ~lowk1) <= g) { kq = k; return 8; } }
-    return 0;
-}
-
-// One candidate (gRNA planes) reached through route r (k_probe: gap position in query coordinates for r >= 5) at candidate
-// window wi.  Stage 1: cheap NECESSARY conditions for "the anchor is problematic and its canonical alignment implies route r
-// (and k_probe)"; a few per cent pass.  An insertion skips one query position, so bounds that use "mismatches on both
-// diagonals" get one unit of slack.  Near a mask the exact verifier decides, so everything passes.
-__device__ __forceinline__ bool sj_stage1(const SjParams& prm, const SjText& T, int wi, int r, int k_probe, uint32_t qlo, uint32_t qhi) {
-    if (!((T.okmask >> wi) & 1u)) return false;
-    if ((T.nearmask >> wi) & 1u) return true;
-    const int o = wi + 1, M = prm.M;
-    const uint32_t D0 = sj_diag(T, qlo, qhi, o);
-    if (r == 2) return __popc(D0) <= M + 1;                                    // R2 only owns ungapped alignments
-    const uint32_t lowk = (1u << k_probe) - 1u;
-    if (r == 5 || r == 7) return __popc(sj_diag(T, qlo, qhi, o - 1) & lowk) + __popc(D0 & ~lowk) <= M;          // the deletion before k fits
-    if (r == 6 || r == 8) return __popc(sj_diag(T, qlo, qhi, o + 1) & lowk) + __popc(D0 & ~(2u * lowk + 1u)) <= M;   // the insertion at k fits
-    if (r == 3) { const uint32_t DM = sj_diag(T, qlo, qhi, o - 1); return __popc(DM & kH1M) + __popc(DM & D0 & kH2M) <= M; }
-    if (r == 4) { const uint32_t DP = sj_diag(T, qlo, qhi, o + 1); return __popc(DP & kH1M) + __popc(DP & D0 & kH2M) <= M + 1; }
-    const uint32_t DM = sj_diag(T, qlo, qhi, o - 1), DP = sj_diag(T, qlo, qhi, o + 1);                           // r == 1
-    return min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1;
-}
-
-// Stage 2 (survivors of stage 1, again 32 at a time): the exact decision and the ownership rule.
+// Stage 2 (the few per cent of the candidates that pass the cheap necessary test of stage 1, again 32 at a time): the exact
+// decision and the ownership rule.  Every lane of the warp must call (the text context comes by shuffle).
 // record: x, y = index entry; z = [3:0] wi, [7:4] route, [12:8] k_probe, [17:13] lane that owns the text context
-__device__ __noinline__ void sj_stage2(const GenomeView& gv, const QueriesView& qv, const GeneralCtx* __restrict__ ctx, const SjParams& prm,
-                                       const SjText* texts, int64_t p_warp, const uint4 rec, uint32_t* __restrict__ counts) {
+__device__ __noinline__ void sj_stage2(int M, int t, SjText T, bool act, uint4 rec, uint32_t* __restrict__ counts) {
     const int wi = (int)(rec.z & 15u), r = (int)((rec.z >> 4) & 15u), k_probe = (int)((rec.z >> 8) & 31u), src = (int)((rec.z >> 13) & 31u);
     const uint32_t qlo = rec.x & kFull, qhi = ((rec.x >> 20) | (rec.y << 12)) & kFull, id = rec.y >> 12;
-    const SjText T = texts[src];
+    const SjText Ts = sj_text_from(T, src);
+    if (!act) return;
     const int o = wi + 1;
-    const uint32_t D0 = sj_diag(T, qlo, qhi, o), DM = sj_diag(T, qlo, qhi, o - 1), DP = sj_diag(T, qlo, qhi, o + 1);
+    const uint32_t D0 = sj_diag(Ts, qlo, qhi, o), DM = sj_diag(Ts, qlo, qhi, o - 1), DP = sj_diag(Ts, qlo, qhi, o + 1);
     int kq = 0;
-    if ((T.nearmask >> wi) & 1u) {
-        const int owner = sj_first_applicable(D0, DM, DP, prm.t, prm.g, kq);
-        if (owner != r || (r >= 5 && kq != k_probe)) return;
-        const int64_t w = p_warp + src - 11 + wi;     // strand window start of the final diagonal
-        if (!verify_anchor(gv, *ctx, qv.codes + (size_t)id * kSjL, qv.packed + id, prm.strand, w + kSjL)) return;
-    } else {
-        const int owner = sj_canonical(D0, DM, DP, prm.M, prm.t, kq);
-        if (owner != r || (r >= 5 && kq != k_probe)) return;
-    }
-    atomicAdd(counts + (prm.strand > 0 ? id : (uint32_t)prm.N + id), 1u);
+    const int owner = sj_canonical(D0, DM, DP, M, t, kq);
+    if (owner != r || (r >= 5 && kq != k_probe)) return;
+    atomicAdd(counts + id, 1u);
 }
 
 // Variant table (the same for every text position): [19:0] substitution mask on the key, [21:20] class (0: the 10-mer at p and
@@ -325,41 +318,43 @@ static std::vector<uint32_t> sj_variants(int t, int g) {
 }
 
 constexpr int kSjWarps = 8;                                  // warps per CTA
-constexpr int kSjQueue = 192;                                // candidate records per warp and queue (16 B each)
-constexpr int kSjRound = 4;                                  // records a lane may append per round
+constexpr int kSjQueue = 160;                                // candidate records per warp and queue (4 B each): < 32 left over + 32 lanes x kSjRound
+constexpr int kSjRound = 4;                                  // records a lane may append per table and round
+constexpr int kSjSurvivors = 64;                             // stage-1 survivors per warp (16 B each): < 32 left over + 32
 
-// The candidate records of a warp are evaluated 32 at a time, one per lane, whatever lane found them: the buckets of the 32
-// text positions of a warp hold 0, 1, 2 ... entries, and evaluating them where they were found would leave most lanes idle.
-// There is one queue per table of the current variant class, so the 32 candidates of a batch take the SAME route (no
-// divergence over the eight routes), and a record carries the index entry itself (loaded by the lane that found it, while the
-// records are being queued), so a batch never waits for memory.  The few per cent that pass stage 1 go to a third queue and
-// are decided 32 at a time as well (the exact evaluation is ~10x the work of stage 1).
-// candidate record: x, y = index entry; z = [3:0] k of a deletion variant, [8:4] lane that owns the text context
-constexpr int kSjSurvivors = 64;
-constexpr size_t kSjSmem = sizeof(uint4) * kSjWarps * (2 * kSjQueue + kSjSurvivors) + sizeof(SjText) * kSjWarps * 32;
-
-__global__ void __launch_bounds__(32 * kSjWarps, 2)
-sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx* __restrict__ ctx, SjParams prm,
-               const uint32_t* __restrict__ variants, int n_variants, int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts) {
-    extern __shared__ uint4 sj_smem[];
+// One warp = 32 consecutive text positions, one lane each; the context of a position (64 bases as bit planes) stays in its
+// lane's registers and travels by shuffle.
+//
+// Classes 0 / 1 (tables 0 / 1, ~1 entry per bucket at 10^6 gRNA).  The buckets of the 32 lanes hold 0, 1, 2 ... entries, and
+// evaluating them where they were found would leave most lanes idle, so the lanes append (entry number, lane, k) records to
+// a per-warp queue in shared memory - one queue per table, so the 32 candidates of a batch take the SAME route - and the
+// queue is evaluated 32 records at a time, one per lane.  A popped batch first only ISSUES its 32 entry loads and is
+// evaluated one variant later, so neither the directory load (issued one variant ahead) nor the entry load is waited for.
+// Class 2 (tables 2 / 3, ~34 entries per bucket at 10^6 gRNA): the warp walks the buckets of one lane after the other, all
+// lanes reading consecutive entries (coalesced), the lane's context broadcast by shuffle; no queue.
+// The few per cent that pass stage 1 go to a survivor queue and are decided 32 at a time as well (sj_stage2).
+__global__ void __launch_bounds__(32 * kSjWarps, 3)
+sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_variants,
+               int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts) {
+    __shared__ uint32_t s_queue[kSjWarps][2][kSjQueue];
+    __shared__ uint4 s_surv[kSjWarps][kSjSurvivors];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4* q0 = sj_smem + (size_t)warp * (2 * kSjQueue + kSjSurvivors);      // this warp's queues
-    uint4* q1 = q0 + kSjQueue;
-    uint4* qs = q1 + kSjQueue;
-    SjText* texts = reinterpret_cast<SjText*>(sj_smem + (size_t)kSjWarps * (2 * kSjQueue + kSjSurvivors)) + warp * 32;
-    const int64_t p_warp = p_begin + ((int64_t)blockIdx.x * kSjWarps + warp) * 32;
-    const int64_t p = p_warp + lane;
+    uint32_t* q0 = s_queue[warp][0];
+    uint32_t* q1 = s_queue[warp][1];
+    uint4* qs = s_surv[warp];
+    const int64_t p = p_begin + ((int64_t)blockIdx.x * kSjWarps + warp) * 32 + lane;
+    const int M = prm.M, t = prm.t;
+    uint32_t* cnt = counts + (prm.strand > 0 ? 0 : prm.N);
     SjText T;
     T.okmask = 0u;
-    T.nearmask = 0u;
-    T.tlo0 = T.tlo1 = T.thi0 = T.thi1 = T.pad0 = T.pad1 = 0u;
+    T.tlo0 = T.tlo1 = T.thi0 = T.thi1 = 0u;
     uint32_t T10 = 0u, U11 = 0u, S9 = 0u;
     if (p < p_end) {
         for (int wi = 0; wi <= 12; ++wi) {
             const int64_t wf = sj_fwd_window(gv, prm.strand, p - 11 + wi);
             if (wf < prm.wb || wf >= prm.we || sj_dirty(gv, wf)) continue;
+            if (gv.n_masks && sj_mask_near(gv, wf - 3, wf + 24)) continue;
             T.okmask |= 1u << wi;
-            if (gv.n_masks && sj_mask_near(gv, wf - 3, wf + 24)) T.nearmask |= 1u << wi;
         }
     }
     if (!__any_sync(0xFFFFFFFFu, T.okmask != 0u)) return;          // the whole warp sits in padding / outside the shard
@@ -372,120 +367,200 @@ sj_scan_kernel(GenomeView gv, QueriesView qv, SeedIndexView ix, const GeneralCtx
         const unsigned long long W = (((unsigned long long)hi0 << 32) | lo0) >> 24;   // 2-bit codes from base p on (20 bases)
         T10 = (uint32_t)W & kFull; U11 = (uint32_t)W & 0x3FFFFFu; S9 = (uint32_t)W & 0x3FFFFu;
     }
-    texts[lane] = T;
-    __syncwarp();
     const bool live = T.okmask != 0u;
     int qlen0 = 0, qlen1 = 0, n_surv = 0;                           // warp-uniform
     int cur_cls = 0;                                                // class of the records in the queues
+    int pend0 = 0, pend1 = 0;                                       // records of the popped batch whose entry loads are in flight
+    uint32_t prec0 = 0u, prec1 = 0u;
+    uint2 pent0 = make_uint2(0u, 0u), pent1 = make_uint2(0u, 0u);
 
-    // stage 1 of one anchor for the 32 candidates of a batch; survivors are compacted into the third queue
-    auto anchor = [&](bool act, const SjText& Tc, const uint4& rec, uint32_t qlo, uint32_t qhi, int src, int wi, int r, int kp) {
-        const bool pass = act && sj_stage1(prm, Tc, wi, r, kp, qlo, qhi);
+    // stage-1 survivors, compacted; a full batch goes through stage 2 at once
+    auto survive = [&](bool pass, const uint2 e, uint32_t meta) {
         const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
         if (m == 0u) return;
-        if (pass) qs[n_surv + __popc(m & ((1u << lane) - 1u))] = make_uint4(rec.x, rec.y, (uint32_t)wi | ((uint32_t)r << 4) | ((uint32_t)kp << 8) | ((uint32_t)src << 13), 0u);
+        if (pass) qs[n_surv + __popc(m & ((1u << lane) - 1u))] = make_uint4(e.x, e.y, meta, 0u);
         n_surv += __popc(m);
         if (n_surv >= 32) {
             __syncwarp();
-            sj_stage2(gv, qv, ctx, prm, texts, p_warp, qs[n_surv - 32 + lane], counts);
+            sj_stage2(M, t, T, true, qs[n_surv - 32 + lane], cnt);
             n_surv -= 32;
             __syncwarp();
         }
     };
+    auto meta_of = [](int wi, int r, int kp, int src) { return (uint32_t)wi | ((uint32_t)r << 4) | ((uint32_t)kp << 8) | ((uint32_t)src << 13); };
 
-    // evaluate the records of queue j (tables of the current class), 32 at a time (all of them if `all`)
-    auto drain = [&](int j, bool all) {
-        int& qlen = j ? qlen1 : qlen0;
-        const uint4* queue = j ? q1 : q0;
-        while (qlen >= 32 || (all && qlen > 0)) {
-            const int take = qlen < 32 ? qlen : 32;
-            __syncwarp();
-            const bool act = lane < take;
-            const uint4 rec = act ? queue[qlen - take + lane] : make_uint4(0u, 0u, 0u, 0u);
-            const int kv = (int)(rec.z & 15u), src = (int)((rec.z >> 4) & 31u);
-            const uint32_t qlo = rec.x & kFull, qhi = ((rec.x >> 20) | (rec.y << 12)) & kFull;
-            const int ke = (int)((rec.y >> 8) & 15u);               // tables 2 / 3: the position of the half that has no partner in the text
-            const SjText Tc = texts[src];
-            if (cur_cls == 0 && j == 0) {
-                anchor(act, Tc, rec, qlo, qhi, src, 11, 2, 0);      // H1 on the final diagonal: w = p
-                anchor(act, Tc, rec, qlo, qhi, src, 12, 3, 0);      // H1 on w - 1: w = p + 1
-                anchor(act, Tc, rec, qlo, qhi, src, 10, 4, 0);      // H1 on w + 1: w = p - 1
-            } else if (cur_cls == 0) anchor(act, Tc, rec, qlo, qhi, src, 1, 1, 0);              // H2 at p: w = p - 10
-            else if (cur_cls == 1 && j == 0) anchor(act, Tc, rec, qlo, qhi, src, 12, 5, kv);    // deletion before query position k
-            else if (cur_cls == 1) anchor(act, Tc, rec, qlo, qhi, src, 2, 7, 10 + kv);          // w - 1 = p - 10
-            else if (j == 0) anchor(act, Tc, rec, qlo, qhi, src, 10, 6, ke);                    // insertion at query position ke (1..9)
-            else anchor(act, Tc, rec, qlo, qhi, src, 0, 8, 10 + ke);                            // insertion at 10..18: w + 1 = p - 10
-            qlen -= take;
-            __syncwarp();
+    // Stage 1 of the pending batch of queue j: cheap NECESSARY conditions for "the anchor is problematic and its canonical
+    // alignment implies this route (and k)".  An insertion skips one query position, so bounds that use "mismatches on both
+    // diagonals" get one unit of slack.
+    auto eval = [&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const bool act = lane < (j ? pend1 : pend0);
+        const uint32_t rec = j ? prec1 : prec0;
+        const uint2 e = j ? pent1 : pent0;
+        const int src = (int)((rec >> 20) & 31u), kv = (int)((rec >> 25) & 15u);
+        const SjText Ts = sj_text_from(T, src);
+        const uint32_t ok = act ? Ts.okmask : 0u;
+        const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull;
+        if (cur_cls == 0 && j == 0) {
+            // the text's 10-mer at p is H1: on the final diagonal (R2, w = p), on w - 1 (R3, w = p + 1), on w + 1 (R4, w = p - 1)
+            const uint32_t d11 = sj_diag(Ts, qlo, qhi, 11), d12 = sj_diag(Ts, qlo, qhi, 12), d13 = sj_diag(Ts, qlo, qhi, 13);
+            const int c1 = __popc(d12 & kH1M);
+            const bool p2 = ((ok >> 11) & 1u) && __popc(d12) <= M + 1;                           // R2 only owns ungapped alignments
+            const bool p3 = ((ok >> 12) & 1u) && c1 + __popc(d12 & d13 & kH2M) <= M;
+            const bool p4 = ((ok >> 10) & 1u) && c1 + __popc(d12 & d11 & kH2M) <= M + 1;
+            if (__any_sync(0xFFFFFFFFu, p2 || p3 || p4)) {
+                survive(p2, e, meta_of(11, 2, 0, src));
+                survive(p3, e, meta_of(12, 3, 0, src));
+                survive(p4, e, meta_of(10, 4, 0, src));
+            }
+        } else if (cur_cls == 0) {
+            // the 10-mer at p is H2 on the final diagonal (R1): w = p - 10
+            const uint32_t DM = sj_diag(Ts, qlo, qhi, 1), D0 = sj_diag(Ts, qlo, qhi, 2), DP = sj_diag(Ts, qlo, qhi, 3);
+            const bool p1 = ((ok >> 1) & 1u) && min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1;
+            survive(p1, e, meta_of(1, 1, 0, src));
+        } else if (j == 0) {
+            // a deletion before query position k of H1 (R5): H1 starts at p on w - 1, w = p + 1; the deletion must fit
+            const uint32_t lowk = (1u << kv) - 1u;
+            const bool p5 = ((ok >> 12) & 1u) && __popc(sj_diag(Ts, qlo, qhi, 12) & lowk) + __popc(sj_diag(Ts, qlo, qhi, 13) & ~lowk) <= M;
+            survive(p5, e, meta_of(12, 5, kv, src));
+        } else {
+            // a deletion before query position 10 + k (R7): H2's first base is at p on w - 1, w - 1 = p - 10
+            const uint32_t lowk = (1u << (10 + kv)) - 1u;
+            const bool p7 = ((ok >> 2) & 1u) && __popc(sj_diag(Ts, qlo, qhi, 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, 3) & ~lowk) <= M;
+            survive(p7, e, meta_of(2, 7, 10 + kv, src));
         }
+        if (j) pend1 = 0; else pend0 = 0;
     };
+    // take up to 32 records off queue j and issue their entry loads
+    auto pop = [&](auto J) {
+        constexpr int j = decltype(J)::value;
+        int& qlen = j ? qlen1 : qlen0;
+        const int take = qlen < 32 ? qlen : 32;
+        const uint32_t rec = lane < take ? (j ? q1 : q0)[qlen - take + lane] : 0u;
+        const uint2 e = lane < take ? __ldg((j ? ix.entries1 : ix.entries0) + (rec & kFull)) : make_uint2(0u, 0u);
+        if (j) { prec1 = rec; pent1 = e; pend1 = take; } else { prec0 = rec; pent0 = e; pend0 = take; }
+        qlen -= take;
+        __syncwarp();
+    };
+    auto service = [&](auto J) {                                     // keep the queue below one batch
+        constexpr int j = decltype(J)::value;
+        while ((j ? qlen1 : qlen0) >= 32) { if (j ? pend1 : pend0) eval(J); pop(J); }
+    };
+    auto flush = [&](auto J) {
+        constexpr int j = decltype(J)::value;
+        while ((j ? qlen1 : qlen0) > 0 || (j ? pend1 : pend0) > 0) { if (j ? pend1 : pend0) eval(J); if ((j ? qlen1 : qlen0) > 0) pop(J); }
+    };
+    const std::integral_constant<int, 0> J0;
+    const std::integral_constant<int, 1> J1;
 
-    // key and bucket bounds of variant v for this lane in tables ta / ta + 1
-    auto bounds = [&](int v, int& cls, int& ta, uint32_t& tag, uint32_t& a0, uint32_t& b0, uint32_t& a1, uint32_t& b1) {
+    // directory words of variant v (classes 0 / 1) for this lane: issues the load
+    auto dir01 = [&](int v) -> uint2 {
+        if (v >= n01) return make_uint2(0u, 0u);
         const uint32_t d = __ldg(variants + v);
         const uint32_t mask = d & kFull;
-        const int k = (int)((d >> 22) & 15u);
-        cls = (int)((d >> 20) & 3u);
         uint32_t key = T10 ^ mask;
         bool valid = live;
-        ta = 0;
-        if (cls == 1) {
-            // two equal neighbours give the same string whichever is removed: the first one (smaller k) stands for both
+        if ((d >> 20) & 3u) {
+            // the 11-mer at p without its base k; two equal neighbours give the same string whichever is removed: the first one
+            // (smaller k) stands for both
+            const int k = (int)((d >> 22) & 15u);
             valid = valid && ((U11 >> (2 * k)) & 3u) != ((U11 >> (2 * k - 2)) & 3u);
             const uint32_t low = (1u << (2 * k)) - 1u;
             key = ((U11 & low) | ((U11 >> (2 * k + 2)) << (2 * k))) ^ mask;
-        } else if (cls == 2) {
-            key = S9 ^ mask;
-            ta = 2;
         }
-        tag = (uint32_t)k | ((uint32_t)lane << 4);
-        a0 = b0 = a1 = b1 = 0u;
-        if (valid) {
-            a0 = __ldg(ix.start[ta] + key); b0 = __ldg(ix.start[ta] + key + 1);
-            a1 = __ldg(ix.start[ta + 1] + key); b1 = __ldg(ix.start[ta + 1] + key + 1);
-        }
+        return valid ? __ldg(ix.dir01 + key) : make_uint2(0u, 0u);
     };
 
-    int cls, ta;
-    uint32_t tag, a0, b0, a1, b1;
-    bounds(0, cls, ta, tag, a0, b0, a1, b1);
-    for (int v = 0; v < n_variants; ++v) {
-        int ncls = 0, nta = 0;
-        uint32_t ntag = 0u, na0 = 0u, nb0 = 0u, na1 = 0u, nb1 = 0u;
-        if (v + 1 < n_variants) bounds(v + 1, ncls, nta, ntag, na0, nb0, na1, nb1);   // the next variant's loads are in flight meanwhile
-        if (cls != cur_cls) { drain(0, true); drain(1, true); cur_cls = cls; }         // a queue only ever holds one route family
-        while (__any_sync(0xFFFFFFFFu, a0 < b0 || a1 < b1)) {
+    uint2 Bn = dir01(0);
+    for (int v = 0; v < n01; ++v) {
+        const uint32_t d = __ldg(variants + v);
+        const int cls = (int)((d >> 20) & 3u);
+        const uint2 B = Bn;
+        Bn = dir01(v + 1);                                          // in flight while this variant is queued and evaluated
+        if (cls != cur_cls) { flush(J0); flush(J1); cur_cls = cls; }   // a queue only ever holds one route family
+        if (pend0) eval(J0);
+        if (pend1) eval(J1);
+        const uint32_t tag = ((uint32_t)lane << 20) | (((d >> 22) & 15u) << 25);
+        uint32_t a0 = B.x >> kSjCountBits01, n0 = B.x & ((1u << kSjCountBits01) - 1u);
+        uint32_t a1 = B.y >> kSjCountBits01, n1 = B.y & ((1u << kSjCountBits01) - 1u);
+        do {
             // every lane appends up to kSjRound records per table; one scan for both counts (16 bits each)
-            const int h0 = (int)min((uint32_t)kSjRound, b0 - a0), h1 = (int)min((uint32_t)kSjRound, b1 - a1);
+            const int h0 = (int)min((uint32_t)kSjRound, n0), h1 = (int)min((uint32_t)kSjRound, n1);
             int off = h0 | (h1 << 16);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, off, d); if (lane >= d) off += o; }
+            for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, off, dd); if (lane >= dd) off += o; }
             const int total = __shfl_sync(0xFFFFFFFFu, off, 31);
+            if (total == 0) break;
             off -= h0 | (h1 << 16);
             const int o0 = qlen0 + (off & 0xFFFF), o1 = qlen1 + (off >> 16);
-            uint2 e0[kSjRound], e1[kSjRound];
-#pragma unroll
-            for (int j = 0; j < kSjRound; ++j) {                    // the entry loads of a round are in flight together
-                e0[j] = j < h0 ? __ldg(ix.entries[ta] + a0 + j) : make_uint2(0u, 0u);
-                e1[j] = j < h1 ? __ldg(ix.entries[ta + 1] + a1 + j) : make_uint2(0u, 0u);
-            }
 #pragma unroll
             for (int j = 0; j < kSjRound; ++j) {
-                if (j < h0) q0[o0 + j] = make_uint4(e0[j].x, e0[j].y, tag, 0u);
-                if (j < h1) q1[o1 + j] = make_uint4(e1[j].x, e1[j].y, tag, 0u);
+                if (j < h0) q0[o0 + j] = (a0 + j) | tag;
+                if (j < h1) q1[o1 + j] = (a1 + j) | tag;
             }
-            a0 += h0; a1 += h1;
+            a0 += h0; n0 -= h0; a1 += h1; n1 -= h1;
             qlen0 += total & 0xFFFF;
             qlen1 += total >> 16;
-            drain(0, false);
-            drain(1, false);
-        }
-        cls = ncls; ta = nta; tag = ntag; a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
+            __syncwarp();
+            service(J0);
+            service(J1);
+        } while (__any_sync(0xFFFFFFFFu, (n0 | n1) != 0u));
     }
-    drain(0, true);
-    drain(1, true);
+    flush(J0);
+    flush(J1);
+
+    // class 2: the text's 9-mer at p is H1 without its position ke (R6: an insertion at query position ke, H1 starts at p on
+    // w + 1, w = p - 1) or H2 without its position ke (R8: insertion at 10 + ke, w + 1 = p - 10); the insertion must fit
+    auto dir23 = [&](int v) -> uint2 {
+        if (v >= n_variants || !live) return make_uint2(0u, 0u);
+        return __ldg(ix.dir23 + (S9 ^ (__ldg(variants + v) & kFull)));
+    };
+    uint2 Cn = dir23(n01);
+    for (int v = n01; v < n_variants; ++v) {
+        const uint2 C = Cn;
+        Cn = dir23(v + 1);
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, (C.x | C.y) != 0u);
+        if (todo == 0u) continue;
+        uint32_t a2, n2, a3, nn;                                    // bucket of the current lane: table 2 [a2, a2 + n2), table 3 [a3, ...), nn entries in all
+        auto setup = [&](int src, uint32_t& sa2, uint32_t& sn2, uint32_t& sa3, uint32_t& snn) {
+            const uint32_t bx = __shfl_sync(0xFFFFFFFFu, C.x, src), by = __shfl_sync(0xFFFFFFFFu, C.y, src);
+            sa2 = bx >> kSjCountBits23; sn2 = bx & 255u; sa3 = ix.off3 + (by >> kSjCountBits23); snn = sn2 + (by & 255u);
+        };
+        auto load = [&](uint32_t sa2, uint32_t sn2, uint32_t sa3, uint32_t snn, uint32_t base) -> uint2 {
+            const uint32_t i = base + lane;
+            return i < snn ? __ldg(ix.entries23 + (i < sn2 ? sa2 + i : sa3 + (i - sn2))) : make_uint2(0u, 0u);
+        };
+        int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        setup(src, a2, n2, a3, nn);
+        uint2 e = load(a2, n2, a3, nn, 0u);
+        for (;;) {
+            int nsrc = -1;
+            uint32_t na2 = 0u, nn2 = 0u, na3 = 0u, nnn = 0u;
+            uint2 en = make_uint2(0u, 0u);
+            if (todo) {                                             // the next lane's first 32 entries are in flight meanwhile
+                nsrc = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                setup(nsrc, na2, nn2, na3, nnn);
+                en = load(na2, nn2, na3, nnn, 0u);
+            }
+            const SjText Ts = sj_text_from(T, src);
+            for (uint32_t base = 0u; base < nn; base += 32u) {
+                if (base) e = load(a2, n2, a3, nn, base);
+                const uint32_t i = base + lane;
+                const bool t3 = i >= n2;
+                const int ke = (int)((e.y >> 8) & 15u), wi = t3 ? 0 : 10, kp = t3 ? 10 + ke : ke;
+                const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, lowk = (1u << kp) - 1u;
+                const bool pass = i < nn && ((Ts.okmask >> wi) & 1u) &&
+                                  __popc(sj_diag(Ts, qlo, qhi, wi + 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, wi + 1) & ~(2u * lowk + 1u)) <= M;
+                survive(pass, e, meta_of(wi, t3 ? 8 : 6, kp, src));
+            }
+            if (nsrc < 0) break;
+            src = nsrc; a2 = na2; n2 = nn2; a3 = na3; nn = nnn; e = en;
+        }
+    }
     __syncwarp();
-    if (lane < n_surv) sj_stage2(gv, qv, ctx, prm, texts, p_warp, qs[lane], counts);
+    sj_stage2(M, t, T, lane < n_surv, lane < n_surv ? qs[lane] : make_uint4(0u, 0u, 0u, 0u), cnt);
 }
 
 // 32-base blocks of [b0, b1) that hold an invalid base
@@ -550,9 +625,20 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     dev_free(d_n, s); dev_free(d_blocks, s);
     if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     if (n_dirty > cap) return MG_ERR_UNSUPPORTED;      // a very ragged subject: the DP path takes all of it
-    std::sort(blocks.begin(), blocks.end());
-    for (const int64_t b : blocks) {                   // windows w with [w-3, w+23) meeting block b: [32b - 22, 32b + 35)
-        const int64_t a = std::max(wb, 32 * b - 22), z = std::min(we, 32 * b + 35);
+    std::vector<std::pair<int64_t, int64_t>> raw;
+    for (const int64_t b : blocks) raw.emplace_back(32 * b - 22, 32 * b + 35);    // windows w with [w-3, w+23) meeting block b
+    if (g->n_masks > 0) {                              // windows w with [w-3, w+24) meeting a masked interval (sj_mask_near)
+        std::vector<int64_t> ms(g->n_masks), me(g->n_masks);
+        e = cudaMemcpyAsync(ms.data(), g->d_mstart, sizeof(int64_t) * g->n_masks, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(me.data(), g->d_mend_pm, sizeof(int64_t) * g->n_masks, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+        // the running maximum of the ends gives the same union as the ends themselves (the interval that set it starts earlier)
+        for (int i = 0; i < g->n_masks; ++i) raw.emplace_back(ms[i] - 23, me[i] + 3);
+    }
+    std::sort(raw.begin(), raw.end());
+    for (const auto& r : raw) {
+        const int64_t a = std::max(wb, r.first), z = std::min(we, r.second);
         if (a >= z) continue;
         if (!dirty_ranges.empty() && a <= dirty_ranges.back().second) dirty_ranges.back().second = std::max(dirty_ranges.back().second, z);
         else dirty_ranges.emplace_back(a, z);
@@ -563,22 +649,23 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     prm.N = q->n; prm.M = crit->max_mismatch; prm.t = (prm.M + 1) / 2; prm.g = prm.M - prm.t - 1;
     prm.wb = wb; prm.we = we;
     SeedIndexView iv;
-    for (int t = 0; t < kSjTables; ++t) { iv.start[t] = ix->d_start[t]; iv.entries[t] = ix->d_entries[t]; }
+    iv.dir01 = ix->d_dir01; iv.dir23 = ix->d_dir23; iv.entries0 = ix->d_entries0; iv.entries1 = ix->d_entries1;
+    iv.entries23 = ix->d_entries23; iv.off3 = 9u * (uint32_t)std::max(1, ix->n);
     const std::vector<uint32_t> vars = sj_variants(prm.t, prm.g);
+    int n01 = 0;                                       // classes 0 / 1 come first
+    while (n01 < (int)vars.size() && ((vars[n01] >> 20) & 3u) != 2u) ++n01;
     uint32_t* d_vars = nullptr;
     MG_CUDA(dev_alloc((void**)&d_vars, sizeof(uint32_t) * vars.size(), s));
     e = cudaMemcpyAsync(d_vars, vars.data(), sizeof(uint32_t) * vars.size(), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);              // vars lives on this stack frame
     if (e != cudaSuccess) { dev_free(d_vars, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
-    const size_t smem = kSjSmem;
-    e = cudaFuncSetAttribute(sj_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int z = 0; z < 2 && e == cudaSuccess; ++z) {
         prm.strand = z == 0 ? 1 : -1;
         // strand windows of the owned forward windows, then the positions that can reach them (w - 1 .. w + 11)
         const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
-        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, smem, s>>>(gv, q->view(), iv, d_ctx, prm, d_vars, (int)vars.size(), p0, p1, d_counts);
+        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_counts);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
