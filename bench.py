@@ -126,11 +126,15 @@ def choose_grnas(lib_mod, targets_all, n):
                 return out[:n]
     rng = np.random.Generator(np.random.PCG64(1000))
     lut = np.frombuffer(b"ACGT", dtype=np.uint8)
-    while len(out) < n:
-        k = lut[rng.integers(0, 4, size=GRNA_LEN)].tobytes().decode()
-        if k not in seen:
-            seen.add(k)
-            out.append(k)
+    while len(out) < n:                               # in blocks: the north star's set is 10^6 gRNA
+        blob = lut[rng.integers(0, 4, size=(n - len(out) + 64, GRNA_LEN))].tobytes().decode()
+        for i in range(0, len(blob), GRNA_LEN):
+            k = blob[i:i + GRNA_LEN]
+            if k not in seen:
+                seen.add(k)
+                out.append(k)
+                if len(out) >= n:
+                    break
     return out
 
 
@@ -348,6 +352,7 @@ def main():
     # their checksum - SCALE runs prove multi-GPU correctness by printing one value at N = 1, 2, 4, 8
     n = len(grnas)
     steps_cnt, stage2 = _lib.last_screen_stats()
+    sj_cand, sj_surv = _lib.last_seedjoin_stats() if args.gapped else (0, 0)      # of the last timed step (this rank)
     counts_host = counts.cpu().numpy().astype(np.uint32)
     host_counts = counts_host[:n].astype(np.int64) + counts_host[n:].astype(np.int64)
     fails = int((host_counts > 0).sum())
@@ -462,6 +467,44 @@ def main():
     my_bases = sum(clens) * len(my_genomes)
     cells_per_launch = 2.0 * n * my_bases
     achieved = cells_per_launch / (kern_ms / 1e3) / 1e12
+    if args.gapped and sj_cand:
+        # seed-and-join (sj_scan_kernel): the unit of work is a CANDIDATE (an index entry compared with the text), counted by
+        # the kernel itself; the ceiling is one warp instruction per scheduler and cycle over the warp instructions the kernel
+        # executes per 32 candidates (ncu, profiles/r02_seedjoin_ncu.json: probes, queueing and both stages included)
+        f_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_seedjoin_ncu.json")) as fh:
+                prof = json.load(fh)
+            per32 = prof["warp_instructions"] / (prof["candidates"] / 32.0)
+        except (OSError, KeyError, ValueError):
+            prof, per32 = None, None
+        cand_s = sj_cand / (kern_ms / 1e3) / 1e9
+        peak_c = sms * 4 * f_hz * 1e6 * 32.0 / per32 / 1e9 if per32 else None
+        roofline = {"bound": "issue slots", "achieved": cand_s, "peak": peak_c, "unit": "Gcandidate/s",
+                    "frac": cand_s / peak_c if peak_c else None, "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+                    "candidates_per_launch": sj_cand, "stage2_candidates_per_launch": sj_surv,
+                    "candidates_per_cell": sj_cand / cells_per_launch,
+                    "effective_tcell_per_s": achieved,
+                    "warp_instructions_per_32_candidates": per32,
+                    "peak_source": "4 schedulers x %d SMs x %.0f MHz (sampled during the run), one warp instruction each per cycle, over the "
+                                   "kernel's own instruction count per candidate (ncu capture in profiles/)" % (sms, f_hz),
+                    "kernel": "sj_scan_kernel (+ the edit-distance rows kernel and verifier on the windows near N runs, contig ends "
+                              "and masks)", "kernel_ms": kern_ms,
+                    "note": "the screen stays exhaustive: every (gRNA, anchor) that satisfies the criterion is found through the "
+                            "pigeonhole routes of DESIGN.md 4; counts equal the DP path's and the C oracle's (parity_check, tests)"}
+        out = {"metric": "gRNA x Gbp screened/sec (exhaustive, device-timed)", "value": value, "unit": "gRNA*Gbp/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bit planes of 2-bit bases)",
+               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
+               "roofline": roofline, "cpu_baseline": None, "device": name, "int_peaks": int_peaks,
+               "cells_per_s": 2.0 * args.grna * total_bases / (ms_per_step / 1e3), "grna_failed": fails,
+               "counts_checksum": "0x%016x" % checksum, "counts_total": int(host_counts.sum()),
+               "parity_check": parity, "window_shard_check": shard_check,
+               "side_measurement": "north-star criterion (<=4 mm / <=1 gap), not BASELINE.json's bench config"}
+        emit(out)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     if args.gapped:
         # gapped_rows_kernel<20,20>: issue slots per (32 gRNA, text character) from the SASS of the per-character loop, less
         # the cold survivor path; one slot per scheduler and cycle = the measured LOP3+IMAD interleaved rate

@@ -222,6 +222,11 @@ int64_t mg_genome_global_length(const mg_genome* g);
  * loaded and summed the last quarter of the gRNA positions.  Used by bench.py for the roofline accounting. */
 int mg_last_screen_stats(uint64_t* out /* [2] */);
 
+/* Work of the most recent seed-and-join screen on this device (the one-gap criterion on a large gRNA set, see
+ * mg_screen; synchronises): out[0] = candidates, i.e. index entries compared with the text, out[1] = candidates that
+ * passed the first (necessary) test and went through the exact evaluation.  Zero if that path did not run. */
+int mg_last_seedjoin_stats(uint64_t* out /* [2] */);
+
 /* Integer-pipe microbenchmarks used for the roofline denominators of the scan kernel (bench.py):
  * which: 0 = LOP3 (ALU pipe) lane-ops, 1 = shared-memory 32-bit loads (LSU), 2 / 3 = 64- / 128-bit shared-memory
  * loads with the scan's broadcast pattern (4 adjacent entries per warp), 4 = indexed constant-bank loads, 5 / 6 = warp

@@ -26,7 +26,7 @@ EXPORTS = [
     "mg_genome_total_bases", "mg_genome_device_bytes", "mg_genome_decode", "mg_genome_free", "mg_genome_set_masks",
     "mg_mask_find", "mg_enumerate_sites", "mg_queries_create", "mg_queries_count", "mg_queries_length",
     "mg_queries_free", "mg_screen", "mg_screen_host", "mg_genome_contig_global_start", "mg_genome_global_length",
-    "mg_microbench", "mg_last_screen_stats",
+    "mg_microbench", "mg_last_screen_stats", "mg_last_seedjoin_stats",
     "mg_fasta_read", "mg_fasta_n_records", "mg_fasta_name", "mg_fasta_offsets", "mg_fasta_sequence", "mg_fasta_free",
     "mg_genome_from_fasta", "mg_screen_to_host",
     "mg_layout_global_length", "mg_genome_from_ascii_chunk", "mg_genome_from_device_ascii_chunk", "mg_genome_owned_range",
@@ -110,6 +110,7 @@ def lib():
                                  C.POINTER(Pam), vp, vp]
     L.mg_microbench.argtypes = [C.c_int, C.POINTER(C.c_double), vp]
     L.mg_last_screen_stats.argtypes = [C.POINTER(C.c_uint64)]
+    L.mg_last_seedjoin_stats.argtypes = [C.POINTER(C.c_uint64)]
     L.mg_fasta_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.mg_fasta_n_records.argtypes = [vp]
     L.mg_fasta_name.argtypes = [vp, C.c_int]
@@ -420,4 +421,12 @@ def last_screen_stats():
     """(steps, second-stage steps) of the most recent bit-sliced scan launch (see mg_last_screen_stats)."""
     out = (C.c_uint64 * 2)()
     check(lib().mg_last_screen_stats(out), "mg_last_screen_stats")
+    return int(out[0]), int(out[1])
+
+
+def last_seedjoin_stats():
+    """(candidates compared with the text, candidates that reached the exact evaluation) of the most recent seed-and-join
+    screen on this device (see mg_last_seedjoin_stats); (0, 0) if that path did not run."""
+    out = (C.c_uint64 * 2)()
+    check(lib().mg_last_seedjoin_stats(out), "mg_last_seedjoin_stats")
     return int(out[0]), int(out[1])

@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(1024, 1) ubench_shfl(uint32_t* out, int iters)
 
 }  // namespace mg
 
+namespace mg { int seedjoin_stats(uint64_t* out); }
+
 extern "C" {
 
 int mg_last_screen_stats(uint64_t* out) {
@@ -151,6 +153,11 @@ int mg_last_screen_stats(uint64_t* out) {
     const int rc = screen_stats(tmp);
     out[0] = tmp[0]; out[1] = tmp[1];
     return rc;
+}
+
+int mg_last_seedjoin_stats(uint64_t* out) {
+    MG_CHECK_ARG(out != nullptr);
+    return mg::seedjoin_stats(out);
 }
 
 int mg_microbench(int which, double* gops, void* stream) {

@@ -52,12 +52,13 @@ constexpr uint32_t kH1M = 0x3FFu, kH2M = 0xFFC00u, kFull = 0xFFFFFu;
 // an insertion in the gRNA is found by asking for the text's 9-mer instead of trying every inserted base at every position.
 // Entry (8 B): [19:0] low-bit plane of the 20 query bases, [39:20] high-bit plane, [43:40] k (position inside the half),
 // [63:44] gRNA index (< 2^20).
-// Directory: ONE 8-byte word per key for a pair of tables (the same key is always looked up in both), each half =
-// first entry << count bits | entry count; 12 count bits for tables 0 / 1, 8 for tables 2 / 3 (a gRNA set with a fuller
-// bucket - thousands of gRNA sharing a half - stays with the DP path).
+// Directory: ONE 8-byte word per key for a pair of tables (the same key is always looked up in both).  Tables 0 / 1: each
+// half = first entry << 12 | entry count.  Tables 2 / 3 share one entry array in which a key's table-2 entries are followed
+// by its table-3 entries: x = first entry, y = table-2 count | table-3 count << 16.  (A gRNA set with a fuller bucket -
+// thousands of gRNA sharing a half - stays with the DP path.)
 constexpr int kSjTables = 4;
 constexpr uint32_t kSjKeys9 = 1u << 18;
-constexpr int kSjCountBits01 = 12, kSjCountBits23 = 8;
+constexpr int kSjCountBits01 = 12, kSjCountBits23 = 12;
 __host__ __device__ constexpr uint32_t sj_table_keys(int t) { return t < 2 ? kSjKeys : kSjKeys9; }
 
 struct SeedIndex {
@@ -65,7 +66,7 @@ struct SeedIndex {
     uint2* d_dir23 = nullptr;                        // [4^9]  directory of tables 2 / 3
     uint2* d_entries0 = nullptr;                     // [n]
     uint2* d_entries1 = nullptr;                     // [n]
-    uint2* d_entries23 = nullptr;                    // [9n] table 2, then [9n] table 3
+    uint2* d_entries23 = nullptr;                    // [18n] per key: table 2's entries, then table 3's
     int n = 0;
     bool usable = false;                             // false: a gRNA with a non-ACGT base or an overfull bucket (the set stays with the DP path)
     cudaStream_t stream = nullptr;
@@ -77,7 +78,6 @@ struct SeedIndexView {
     const uint2* entries0;
     const uint2* entries1;
     const uint2* entries23;
-    uint32_t off3;                                   // first entry of table 3 in entries23
 };
 
 void seed_index_free(SeedIndex* ix) {
@@ -155,29 +155,47 @@ static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out
         unsigned int bad = 0;
         if ((e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
         bool fits = true;
+        std::vector<uint32_t> h3;
         for (int t = 0; t < kSjTables && e == cudaSuccess; ++t) {
             // exclusive scan on the host: <= 4 MB per table, once per gRNA set
             const size_t nk = (size_t)sj_table_keys(t), kb = sizeof(uint32_t) * nk;
-            const int bits = t < 2 ? kSjCountBits01 : kSjCountBits23;
             if ((e = cudaMemcpyAsync(h.data(), d_cur[t], kb, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
-            uint32_t run = 0;
-            for (size_t k = 0; k < nk; ++k) {
-                const uint32_t c = h[k];
-                if (c >= (1u << bits)) fits = false;
-                const uint32_t word = c ? (run << bits) | c : 0u;
-                if (t & 1) dir[k].y = word; else dir[k].x = word;
-                h[k] = run;
-                run += c;
+            if (t < 2) {
+                uint32_t run = 0;
+                for (size_t k = 0; k < nk; ++k) {
+                    const uint32_t c = h[k];
+                    if (c >= (1u << kSjCountBits01)) fits = false;
+                    const uint32_t word = c ? (run << kSjCountBits01) | c : 0u;
+                    if (t & 1) dir[k].y = word; else dir[k].x = word;
+                    h[k] = run;
+                    run += c;
+                }
+                if ((e = cudaMemcpyAsync(d_cur[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+                if (t == 1) e = cudaMemcpyAsync(ix->d_dir01, dir.data(), sizeof(uint2) * nk, cudaMemcpyHostToDevice, s);
+            } else if (t == 2) {
+                h3.assign(h.begin(), h.begin() + nk);            // table 2's counts wait for table 3's
+                continue;
+            } else {
+                uint32_t run = 0;
+                for (size_t k = 0; k < nk; ++k) {
+                    const uint32_t c2 = h3[k], c3 = h[k];
+                    if (c2 >= (1u << kSjCountBits23) || c3 >= (1u << kSjCountBits23)) fits = false;
+                    dir[k] = make_uint2(run, c2 | (c3 << 16));
+                    h3[k] = run;                                 // cursor of table 2
+                    h[k] = run + c2;                             // cursor of table 3
+                    run += c2 + c3;
+                }
+                if ((e = cudaMemcpyAsync(d_cur[2], h3.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+                if ((e = cudaMemcpyAsync(d_cur[3], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+                e = cudaMemcpyAsync(ix->d_dir23, dir.data(), sizeof(uint2) * nk, cudaMemcpyHostToDevice, s);
             }
-            if ((e = cudaMemcpyAsync(d_cur[t], h.data(), kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
-            if (t & 1) e = cudaMemcpyAsync(t == 1 ? ix->d_dir01 : ix->d_dir23, dir.data(), sizeof(uint2) * nk, cudaMemcpyHostToDevice, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         }
         if (e != cudaSuccess) break;
         ix->usable = bad == 0 && fits;
         if (ix->usable && grid) sj_index_kernel<<<grid, 256, 0, s>>>(q->d_packed, q->n, 1, d_cur[0], d_cur[1], d_cur[2], d_cur[3], ix->d_entries0,
-                                                                     ix->d_entries1, ix->d_entries23, ix->d_entries23 + 9 * n1, d_bad);
+                                                                     ix->d_entries1, ix->d_entries23, ix->d_entries23, d_bad);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     } while (0);
@@ -335,7 +353,7 @@ constexpr int kSjSurvivors = 64;                             // stage-1 survivor
 // The few per cent that pass stage 1 go to a survivor queue and are decided 32 at a time as well (sj_stage2).
 __global__ void __launch_bounds__(32 * kSjWarps, 3)
 sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_variants,
-               int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts) {
+               int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
     __shared__ uint32_t s_queue[kSjWarps][2][kSjQueue];
     __shared__ uint4 s_surv[kSjWarps][kSjSurvivors];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,17 +387,19 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
     }
     const bool live = T.okmask != 0u;
     int qlen0 = 0, qlen1 = 0, n_surv = 0;                           // warp-uniform
+    unsigned int st_cand = 0u, st_surv = 0u;                        // candidates looked at / stage-1 survivors (mg_last_seedjoin_stats)
     int cur_cls = 0;                                                // class of the records in the queues
     int pend0 = 0, pend1 = 0;                                       // records of the popped batch whose entry loads are in flight
     uint32_t prec0 = 0u, prec1 = 0u;
     uint2 pent0 = make_uint2(0u, 0u), pent1 = make_uint2(0u, 0u);
 
     // stage-1 survivors, compacted; a full batch goes through stage 2 at once
-    auto survive = [&](bool pass, const uint2 e, uint32_t meta) {
+    auto survive = [&](bool pass, const uint2 e, int wi, int r, int kp, int src) {
         const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
         if (m == 0u) return;
-        if (pass) qs[n_surv + __popc(m & ((1u << lane) - 1u))] = make_uint4(e.x, e.y, meta, 0u);
+        if (pass) qs[n_surv + __popc(m & ((1u << lane) - 1u))] = make_uint4(e.x, e.y, (uint32_t)wi | ((uint32_t)r << 4) | ((uint32_t)kp << 8) | ((uint32_t)src << 13), 0u);
         n_surv += __popc(m);
+        st_surv += __popc(m);
         if (n_surv >= 32) {
             __syncwarp();
             sj_stage2(M, t, T, true, qs[n_surv - 32 + lane], cnt);
@@ -387,7 +407,6 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
             __syncwarp();
         }
     };
-    auto meta_of = [](int wi, int r, int kp, int src) { return (uint32_t)wi | ((uint32_t)r << 4) | ((uint32_t)kp << 8) | ((uint32_t)src << 13); };
 
     // Stage 1 of the pending batch of queue j: cheap NECESSARY conditions for "the anchor is problematic and its canonical
     // alignment implies this route (and k)".  An insertion skips one query position, so bounds that use "mismatches on both
@@ -409,25 +428,25 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
             const bool p3 = ((ok >> 12) & 1u) && c1 + __popc(d12 & d13 & kH2M) <= M;
             const bool p4 = ((ok >> 10) & 1u) && c1 + __popc(d12 & d11 & kH2M) <= M + 1;
             if (__any_sync(0xFFFFFFFFu, p2 || p3 || p4)) {
-                survive(p2, e, meta_of(11, 2, 0, src));
-                survive(p3, e, meta_of(12, 3, 0, src));
-                survive(p4, e, meta_of(10, 4, 0, src));
+                survive(p2, e, 11, 2, 0, src);
+                survive(p3, e, 12, 3, 0, src);
+                survive(p4, e, 10, 4, 0, src);
             }
         } else if (cur_cls == 0) {
             // the 10-mer at p is H2 on the final diagonal (R1): w = p - 10
             const uint32_t DM = sj_diag(Ts, qlo, qhi, 1), D0 = sj_diag(Ts, qlo, qhi, 2), DP = sj_diag(Ts, qlo, qhi, 3);
             const bool p1 = ((ok >> 1) & 1u) && min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1;
-            survive(p1, e, meta_of(1, 1, 0, src));
+            survive(p1, e, 1, 1, 0, src);
         } else if (j == 0) {
             // a deletion before query position k of H1 (R5): H1 starts at p on w - 1, w = p + 1; the deletion must fit
             const uint32_t lowk = (1u << kv) - 1u;
             const bool p5 = ((ok >> 12) & 1u) && __popc(sj_diag(Ts, qlo, qhi, 12) & lowk) + __popc(sj_diag(Ts, qlo, qhi, 13) & ~lowk) <= M;
-            survive(p5, e, meta_of(12, 5, kv, src));
+            survive(p5, e, 12, 5, kv, src);
         } else {
             // a deletion before query position 10 + k (R7): H2's first base is at p on w - 1, w - 1 = p - 10
             const uint32_t lowk = (1u << (10 + kv)) - 1u;
             const bool p7 = ((ok >> 2) & 1u) && __popc(sj_diag(Ts, qlo, qhi, 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, 3) & ~lowk) <= M;
-            survive(p7, e, meta_of(2, 7, 10 + kv, src));
+            survive(p7, e, 2, 7, 10 + kv, src);
         }
         if (j) pend1 = 0; else pend0 = 0;
     };
@@ -501,6 +520,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
             a0 += h0; n0 -= h0; a1 += h1; n1 -= h1;
             qlen0 += total & 0xFFFF;
             qlen1 += total >> 16;
+            st_cand += (total & 0xFFFF) + (total >> 16);
             __syncwarp();
             service(J0);
             service(J1);
@@ -515,52 +535,61 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         if (v >= n_variants || !live) return make_uint2(0u, 0u);
         return __ldg(ix.dir23 + (S9 ^ (__ldg(variants + v) & kFull)));
     };
-    uint2 Cn = dir23(n01);
-    for (int v = n01; v < n_variants; ++v) {
-        const uint2 C = Cn;
-        Cn = dir23(v + 1);
-        unsigned todo = __ballot_sync(0xFFFFFFFFu, (C.x | C.y) != 0u);
-        if (todo == 0u) continue;
-        uint32_t a2, n2, a3, nn;                                    // bucket of the current lane: table 2 [a2, a2 + n2), table 3 [a3, ...), nn entries in all
-        auto setup = [&](int src, uint32_t& sa2, uint32_t& sn2, uint32_t& sa3, uint32_t& snn) {
-            const uint32_t bx = __shfl_sync(0xFFFFFFFFu, C.x, src), by = __shfl_sync(0xFFFFFFFFu, C.y, src);
-            sa2 = bx >> kSjCountBits23; sn2 = bx & 255u; sa3 = ix.off3 + (by >> kSjCountBits23); snn = sn2 + (by & 255u);
-        };
-        auto load = [&](uint32_t sa2, uint32_t sn2, uint32_t sa3, uint32_t snn, uint32_t base) -> uint2 {
-            const uint32_t i = base + lane;
-            return i < snn ? __ldg(ix.entries23 + (i < sn2 ? sa2 + i : sa3 + (i - sn2))) : make_uint2(0u, 0u);
-        };
-        int src = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        setup(src, a2, n2, a3, nn);
-        uint2 e = load(a2, n2, a3, nn, 0u);
-        for (;;) {
-            int nsrc = -1;
-            uint32_t na2 = 0u, nn2 = 0u, na3 = 0u, nnn = 0u;
-            uint2 en = make_uint2(0u, 0u);
-            if (todo) {                                             // the next lane's first 32 entries are in flight meanwhile
-                nsrc = __ffs(todo) - 1;
-                todo &= todo - 1u;
-                setup(nsrc, na2, nn2, na3, nnn);
-                en = load(na2, nn2, na3, nnn, 0u);
+    // Work items = (lane whose bucket is walked, 32 consecutive entries of it); the entries of the next two items are in flight
+    // while one is evaluated.
+    struct Item { int src; uint32_t base, n2, nn; uint2 e; };
+    int v2 = n01 - 1;                                               // generator state (warp-uniform but for C)
+    uint2 C = make_uint2(0u, 0u), Cn = dir23(n01);
+    unsigned todo = 0u;
+    int g_src = -1;
+    uint32_t g_base = 0u, g_a = 0u, g_n2 = 0u, g_nn = 0u;
+    auto next = [&](Item& it) {
+        it.src = -1;
+        if (g_src >= 0 && g_base + 32u < g_nn) {
+            g_base += 32u;
+        } else {
+            while (todo == 0u) {                                    // next variant with a non-empty bucket
+                if (++v2 >= n_variants) { g_src = -1; return; }
+                C = Cn;
+                Cn = dir23(v2 + 1);
+                todo = __ballot_sync(0xFFFFFFFFu, C.y != 0u);
             }
-            const SjText Ts = sj_text_from(T, src);
-            for (uint32_t base = 0u; base < nn; base += 32u) {
-                if (base) e = load(a2, n2, a3, nn, base);
-                const uint32_t i = base + lane;
-                const bool t3 = i >= n2;
-                const int ke = (int)((e.y >> 8) & 15u), wi = t3 ? 0 : 10, kp = t3 ? 10 + ke : ke;
-                const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, lowk = (1u << kp) - 1u;
-                const bool pass = i < nn && ((Ts.okmask >> wi) & 1u) &&
-                                  __popc(sj_diag(Ts, qlo, qhi, wi + 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, wi + 1) & ~(2u * lowk + 1u)) <= M;
-                survive(pass, e, meta_of(wi, t3 ? 8 : 6, kp, src));
-            }
-            if (nsrc < 0) break;
-            src = nsrc; a2 = na2; n2 = nn2; a3 = na3; nn = nnn; e = en;
+            g_src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t by = __shfl_sync(0xFFFFFFFFu, C.y, g_src);
+            g_a = __shfl_sync(0xFFFFFFFFu, C.x, g_src); g_n2 = by & 0xFFFFu; g_nn = g_n2 + (by >> 16);
+            g_base = 0u;
+            st_cand += g_nn;
         }
+        const uint32_t i = g_base + lane;
+        it.src = g_src; it.base = g_base; it.n2 = g_n2; it.nn = g_nn;
+        it.e = i < g_nn ? __ldg(ix.entries23 + g_a + i) : make_uint2(0u, 0u);
+    };
+    int t_src = -1;
+    SjText Ts = T;
+    auto process = [&](const Item& it) {
+        if (it.src != t_src) { Ts = sj_text_from(T, it.src); t_src = it.src; }
+        const uint32_t i = it.base + lane;
+        const bool t3 = i >= it.n2;
+        const int ke = (int)((it.e.y >> 8) & 15u), wi = t3 ? 0 : 10, kp = t3 ? 10 + ke : ke;
+        const uint32_t qlo = it.e.x & kFull, qhi = ((it.e.x >> 20) | (it.e.y << 12)) & kFull, lowk = (1u << kp) - 1u;
+        const bool pass = i < it.nn && ((Ts.okmask >> wi) & 1u) &&
+                          __popc(sj_diag(Ts, qlo, qhi, wi + 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, wi + 1) & ~(2u * lowk + 1u)) <= M;
+        survive(pass, it.e, wi, t3 ? 8 : 6, kp, it.src);
+    };
+    Item A, B1, B2;
+    next(A);
+    next(B1);
+    while (A.src >= 0) {
+        B2.src = -1;
+        if (B1.src >= 0) next(B2);
+        process(A);
+        A = B1;
+        B1 = B2;
     }
     __syncwarp();
     sj_stage2(M, t, T, lane < n_surv, lane < n_surv ? qs[lane] : make_uint4(0u, 0u, 0u, 0u), cnt);
+    if (lane == 0) { atomicAdd(stats, (unsigned long long)st_cand); atomicAdd(stats + 1, (unsigned long long)st_surv); }
 }
 
 // 32-base blocks of [b0, b1) that hold an invalid base
@@ -574,6 +603,28 @@ __global__ void sj_dirty_blocks_kernel(GenomeView gv, int64_t b0, int64_t b1, un
     }
 }
 
+// [0] candidates (index entries compared with the text), [1] stage-1 survivors of the launches since the last reset, per device
+constexpr int kSjMaxDevices = 64;
+static unsigned long long* g_sj_stats[kSjMaxDevices] = {nullptr};
+
+static int sj_stats_buffer(unsigned long long** out) {
+    int dev = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kSjMaxDevices) { set_error("device index %d out of range", dev); return MG_ERR_ARG; }
+    if (!g_sj_stats[dev]) MG_CUDA(cudaMalloc(&g_sj_stats[dev], 16));
+    *out = g_sj_stats[dev];
+    return MG_OK;
+}
+
+int seedjoin_stats(uint64_t* out) {
+    int dev = 0;
+    out[0] = out[1] = 0;
+    MG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kSjMaxDevices || !g_sj_stats[dev]) return MG_OK;
+    MG_CUDA(cudaMemcpy(out, g_sj_stats[dev], 16, cudaMemcpyDeviceToHost));
+    return MG_OK;
+}
+
 // Can this screen use the seed-and-join path?  (criterion class, gRNA length, set size; MG_GAPPED=dp|seedjoin overrides the size rule)
 bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
     if (crit->n_units != 0 || crit->max_gap != 1 || !crit->pamless || q->len != kSjL) return false;
@@ -581,7 +632,7 @@ bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
     const char* env = getenv("MG_GAPPED");
     if (env && strcmp(env, "dp") == 0) return false;
     if (env && strcmp(env, "seedjoin") == 0) return true;
-    long long min_n = 150000;                          // below this the bit-sliced DP is faster (the probes do not depend on N)
+    long long min_n = 40000;                           // below this the bit-sliced DP is faster (the ~740 probes per position do not depend on N)
     if (const char* m = getenv("MG_SEEDJOIN_MIN")) min_n = atoll(m);
     return q->n >= min_n;
 }
@@ -599,6 +650,9 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     }
     const SeedIndex* ix = q->sj;
     if (!ix->usable) return MG_ERR_UNSUPPORTED;
+    unsigned long long* d_stats = nullptr;
+    { const int rc = sj_stats_buffer(&d_stats); if (rc != MG_OK) return rc; }
+    MG_CUDA(cudaMemsetAsync(d_stats, 0, 16, s));
     const GenomeView gv = g->view();
     // dirty 32-base blocks around the owned windows -> window ranges for the DP path
     const int64_t b0 = std::max<int64_t>(0, (wb - 3) >> 5), b1 = std::min<int64_t>(g->glen >> 5, ((we + 22) >> 5) + 1);
@@ -650,7 +704,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     prm.wb = wb; prm.we = we;
     SeedIndexView iv;
     iv.dir01 = ix->d_dir01; iv.dir23 = ix->d_dir23; iv.entries0 = ix->d_entries0; iv.entries1 = ix->d_entries1;
-    iv.entries23 = ix->d_entries23; iv.off3 = 9u * (uint32_t)std::max(1, ix->n);
+    iv.entries23 = ix->d_entries23;
     const std::vector<uint32_t> vars = sj_variants(prm.t, prm.g);
     int n01 = 0;                                       // classes 0 / 1 come first
     while (n01 < (int)vars.size() && ((vars[n01] >> 20) & 3u) != 2u) ++n01;
@@ -665,7 +719,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
-        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_counts);
+        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_counts, d_stats);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }

@@ -56,20 +56,24 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / 1e3, c.clone()
-        run("seedjoin", 0, 1 << 20)                                  # builds the index, warms up
+        run("seedjoin", 0, 1 << 20)                                  # builds the index, warms up (the two launches an ncu capture takes)
+        warm_stats = _lib.last_seedjoin_stats()
         glen = genome.global_length
         if frac >= 1.0:
             t_sj, c_sj = run("seedjoin")
         else:
             t_part, c_sj = run("seedjoin", glen // 4, glen // 4 + int(glen * frac))
             t_sj = t_part / frac
+        cand, surv = _lib.last_seedjoin_stats()
         a, b = glen // 2, glen // 2 + glen // 64
         t_sj_part, c_sj_part = run("seedjoin", a, b)
         t_dp_part, c_dp_part = run("dp", a, b)
         equal = bool(torch.equal(c_sj_part, c_dp_part))
         print(json.dumps({"n_grna": n, "genome_bp": total, "criterion": "<=4 mismatches / <=1 gap, both strands, no pattern, PAM-less",
                           "seedjoin_seconds": t_sj, "timed_fraction_of_genome": frac, "seedjoin_tcell_per_s": 2.0 * n * total / t_sj / 1e12,
-                          "anchors_total": int(c_sj.sum().item()),
+                          "anchors_total": int(c_sj.sum().item()), "candidates": cand, "stage2_candidates": surv,
+                          "candidates_per_cell": cand / (2.0 * n * total * min(frac, 1.0)),
+                          "warmup_range_candidates": warm_stats[0], "warmup_range_stage2_candidates": warm_stats[1],
                           "range_windows": b - a, "seedjoin_seconds_on_range": t_sj_part, "dp_seconds_on_range": t_dp_part,
                           "dp_seconds_whole_genome_extrapolated": t_dp_part * glen / (b - a),
                           "speedup_on_range": t_dp_part / t_sj_part, "counts_equal_on_range": equal,
