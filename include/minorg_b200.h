@@ -192,7 +192,11 @@ typedef struct {
  * gRNA i fails the background check iff d_counts[i] + d_counts[N+i] > 0.  No early exit: every cell is
  * evaluated, and the counts are exact in every mode: each problematic anchor (strand, virtual alignment end) is counted once,
  * whatever prefilter found it and however the window range is cut into shards or slices.  window range [win_begin, win_end) in global coordinates selects a shard (pass 0, -1 for all).
- * pam may be NULL when crit->pamless. */
+ * pam may be NULL when crit->pamless.
+ * Algorithm by criterion (same counts whichever runs): no gap -> bit-sliced pair-word scan; gaps or a pattern -> a prefilter
+ * (bit-sliced edit distance, or exact pieces) + the exact verifier; no pattern, <= 1 gap, <= 4 mismatches, PAM-less, 20-nt gRNA
+ * and a set of >= 40 000 gRNA (environment MG_SEEDJOIN_MIN; MG_GAPPED=dp|seedjoin forces either) -> the seed-and-join screen,
+ * which builds a hash index of the gRNA set on first use and keeps it in the mg_queries handle (~170 B per gRNA). */
 int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
               int64_t win_begin, int64_t win_end, uint32_t* d_counts, void* stream);
 
