@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the gapped / pattern side measurements (N=1 only)")
     ap.add_argument("--no-checks", action="store_true", help="skip the oracle parity slice and the window-shard check")
+    ap.add_argument("--north-star-grna", type=int, default=1_000_000,
+                    help="N=1 side measurement: gRNA count of the north-star criterion (<=4 mm / <=1 gap) on genome 0 alone (0 = skip)")
     ap.add_argument("--gapped", action="store_true",
                     help="NOT the BASELINE config: time the north star's <=4 mismatches / <=1 gap criterion on the same genomes "
                          "(edit-distance rows kernel + verifier); implies --no-cpu-baseline --no-other-modes")
@@ -407,6 +409,39 @@ def main():
             other_modes.append(entry)
             if q_sub is not queries:
                 q_sub.free()
+        if args.north_star_grna > 0:
+            # the north star's own job, one GPU's share of it: 10^6 gRNA against ONE of the genomes, <=4 mm / <=1 gap (the
+            # seed-and-join screen; on 8 GPUs each rank does exactly this: profiles/r02_bench_gapped_seedjoin_n8.json)
+            n_ns = args.north_star_grna
+            g_ns = choose_grnas(_lib, targets_all, n_ns)
+            q_ns = _lib.Queries(g_ns, stream=stream)
+            c_ns = torch.zeros(2 * n_ns, dtype=torch.int32, device=device)
+            crit_ns = make_criteria(ot_mismatch=MAX_MISMATCH + 1, ot_gap=2, grna_length=GRNA_LEN)
+            # genome 0's windows: from the padding before its first contig (anchors that hang off the contig start belong to
+            # windows there) to half-way into the >= 64 invalid bases before the next genome's first contig
+            w0 = 0
+            w1 = genome.contig_global_start(len(clens)) - 32 if len(my_genomes) > 1 else -1
+            _lib.screen(genome, q_ns, crit_ns, None, c_ns.data_ptr(), win_begin=w0, win_end=w0 + (1 << 20), stream=stream)   # builds the index
+            torch.cuda.synchronize()
+            c_ns.zero_()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            _lib.screen(genome, q_ns, crit_ns, None, c_ns.data_ptr(), win_begin=w0, win_end=w1, stream=stream)
+            m1.record()
+            torch.cuda.synchronize()
+            sec = m0.elapsed_time(m1) / 1e3
+            cand, surv = _lib.last_seedjoin_stats()
+            entry = {"mode": "north star on one GPU: %d gRNA x genome 0 (%d bp), <=4 mismatches / <=1 gap (seed-and-join screen; the "
+                             "8-GPU job is this on every rank)" % (n_ns, sum(clens)), "n_grna": n_ns, "seconds": sec,
+                     "value": n_ns * sum(clens) / 1e9 / sec, "unit": "gRNA*Gbp/s", "tcell_per_s": 2.0 * n_ns * sum(clens) / sec / 1e12,
+                     "candidates": cand, "stage2_candidates": surv, "candidates_per_cell": cand / (2.0 * n_ns * sum(clens)),
+                     "anchors_total": int(c_ns.sum(dtype=torch.int64).item())}
+            if not args.no_checks:
+                entry["parity_check"] = general_parity(torch, _lib, genome, q_ns, crit_ns, g_ns, masks, ascii_dev, clens, threads, stream,
+                                                       device, span=20000, n_sub=256, ot_gap=2, max_mismatch=MAX_MISMATCH)
+            other_modes.append(entry)
+            q_ns.free()
+            del c_ns
 
     # ---- end-to-end through the host-buffer C-ABI call (H2D + pack + tables + screen + D2H)
     e2e = None

@@ -144,3 +144,48 @@ def test_seedjoin_chunks_and_non_acgt_grna(L):
     finally:
         q.free()
         whole.free()
+
+
+def test_seedjoin_default_selection_stats_and_degenerate_sets(L):
+    """Without MG_GAPPED the path is chosen by the set size (MG_SEEDJOIN_MIN); the kernel's own counters say which ran.
+    A set in which thousands of gRNA share a 10-base half overflows a bucket's count field: the index is unusable and the
+    DP path takes the whole set.  Duplicate gRNA are separate queries with equal counts."""
+    import torch
+    from minorg_b200.ot_regex import make_criteria
+    contigs, grnas = _world(21, 1500, [60000, 30000], n_runs=False)
+    genome = L.Genome.from_contigs(contigs)
+    crit = make_criteria(ot_mismatch=5, ot_gap=2, grna_length=20)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def plain(q):
+        c = torch.zeros(2 * q.n, dtype=torch.int32, device="cuda")
+        L.screen(genome, q, crit, None, c.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        return c.cpu().numpy().astype(np.int64)
+
+    os.environ.pop("MG_GAPPED", None)
+    q = L.Queries(grnas + grnas[:7])
+    try:
+        want = _counts(L, genome, q, crit, "dp")
+        os.environ["MG_SEEDJOIN_MIN"] = "1000"
+        _counts(L, genome, q, crit, "dp")                     # resets nothing: the counters belong to the seed-and-join launches
+        got = plain(q)
+        cand, surv = L.last_seedjoin_stats()
+        assert np.array_equal(got, want)
+        assert cand > 0 and 0 < surv < cand
+        assert np.array_equal(got[:7], got[1500:1507]) and np.array_equal(got[q.n:q.n + 7], got[q.n + 1500:q.n + 1507])
+        os.environ["MG_SEEDJOIN_MIN"] = "100000"              # above the set size: the DP path, same counts
+        assert np.array_equal(plain(q), want)
+    finally:
+        os.environ.pop("MG_SEEDJOIN_MIN", None)
+        q.free()
+    # 5 000 gRNA with the same first half: bucket of table 0 holds 5 000 > 4 095 entries
+    rng = random.Random(5)
+    half = contigs[0][1][1000:1010].upper()
+    shared = [half + _contig(rng, 10) for _ in range(5000)]
+    q = L.Queries(shared)
+    try:
+        assert np.array_equal(_counts(L, genome, q, crit, "seedjoin"), _counts(L, genome, q, crit, "dp"))
+    finally:
+        q.free()
+        genome.free()
