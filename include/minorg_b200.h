@@ -194,9 +194,10 @@ typedef struct {
  * whatever prefilter found it and however the window range is cut into shards or slices.  window range [win_begin, win_end) in global coordinates selects a shard (pass 0, -1 for all).
  * pam may be NULL when crit->pamless.
  * Algorithm by criterion (same counts whichever runs): no gap -> bit-sliced pair-word scan; gaps or a pattern -> a prefilter
- * (bit-sliced edit distance, or exact pieces) + the exact verifier; no pattern, <= 1 gap, <= 4 mismatches, PAM-less, 20-nt gRNA
- * and a set of >= 40 000 gRNA (environment MG_SEEDJOIN_MIN; MG_GAPPED=dp|seedjoin forces either) -> the seed-and-join screen,
- * which builds a hash index of the gRNA set on first use and keeps it in the mg_queries handle (~170 B per gRNA). */
+ * (bit-sliced edit distance, or exact pieces) + the exact verifier; no pattern, <= 1 gap, <= 4 mismatches (<= 5 without gap),
+ * PAM-less, 20-nt gRNA and a large set (>= 40 000 gRNA with a gap, >= 100 000 without; environment MG_SEEDJOIN_MIN, and
+ * MG_SEEDJOIN=off|on forces either) -> the seed-and-join screen, which builds a hash index of the gRNA set on first use and
+ * keeps it in the mg_queries handle (~170 B per gRNA). */
 int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,
               int64_t win_begin, int64_t win_end, uint32_t* d_counts, void* stream);
 

@@ -143,7 +143,13 @@ __global__ void __launch_bounds__(1024, 1) ubench_shfl(uint32_t* out, int iters)
 
 }  // namespace mg
 
-namespace mg { int seedjoin_stats(uint64_t* out); }
+namespace mg {
+struct GeneralCtx;
+int seedjoin_stats(uint64_t* out);
+bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit);
+int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const GeneralCtx* d_ctx, int64_t wb, int64_t we,
+                    uint32_t* d_counts, cudaStream_t s, std::vector<std::pair<int64_t, int64_t>>& dirty_ranges);
+}
 
 extern "C" {
 
@@ -218,6 +224,20 @@ int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, 
     const bool fast = crit->n_units == 0 && crit->max_gap == 0 && crit->pamless;
     if (fast) {
         if (crit->max_mismatch >= L) { set_error("mismatch budget %d >= gRNA length %d", crit->max_mismatch, L); return MG_ERR_ARG; }
+        if (mg::seedjoin_eligible(q, crit)) {
+            // a large gRNA set: the seed-and-join screen counts every window whose surroundings are clean and away from masks;
+            // the pair-word scan takes the rest as window ranges (same counts either way)
+            std::vector<std::pair<int64_t, int64_t>> dirty;
+            const int r2 = mg::launch_seedjoin(g, q, crit, nullptr, win_begin, win_end, d_counts, s, dirty);
+            if (r2 == MG_OK) {
+                for (const auto& r : dirty) {
+                    const int r3 = launch_screen_bitsliced(g, q, crit->max_mismatch, r.first, r.second, d_counts, s);
+                    if (r3 != MG_OK) return r3;
+                }
+                return MG_OK;
+            }
+            if (r2 != MG_ERR_UNSUPPORTED) return r2;
+        }
         return launch_screen_bitsliced(g, q, crit->max_mismatch, win_begin, win_end, d_counts, s);
     }
     return launch_screen_general(g, q, crit, pam, win_begin, win_end, d_counts, s);

@@ -208,6 +208,7 @@ static int seed_index_build(const mg_queries* q, cudaStream_t s, SeedIndex** out
 // ------------------------------------------------------------------------------------------------ scan
 struct SjParams {
     int N, M, t, g;            // gRNA count, mismatch budget, pigeonhole thresholds
+    int gapless;               // 1: the criterion allows no gap (Hamming <= M): routes R1 / R2 only
     int strand;
     int64_t wb, we;            // forward window starts owned by this call
 };
@@ -262,9 +263,10 @@ __device__ __forceinline__ uint32_t sj_diag(const SjText& T, uint32_t qlo, uint3
 }
 
 // The canonical alignment of a clean, unmasked anchor and the route it implies (0: the anchor is not problematic).
-__device__ __noinline__ int sj_canonical(uint32_t D0, uint32_t DM, uint32_t DP, int M, int t, int& kq) {
+__device__ __noinline__ int sj_canonical(uint32_t D0, uint32_t DM, uint32_t DP, int M, int t, bool gapless, int& kq) {
     const int h = __popc(D0), c2 = __popc(D0 & kH2M);
     kq = 0;
+    if (gapless) return h <= M ? (c2 <= t ? 1 : 2) : 0;          // no gap budget: a trimmed end costs what its mismatch cost
     if (h <= M || (h == M + 1 && (D0 & 0x80001u))) return c2 <= t ? 1 : 2;
     int a = 0, b = h;                                 // deletion before k: #mm(DM, [0,k)) + #mm(D0, [k,20))
     for (int k = 1; k <= 19; ++k) {
@@ -293,7 +295,7 @@ __device__ __noinline__ int sj_canonical(uint32_t D0, uint32_t DM, uint32_t DP, 
 // Stage 2 (the few per cent of the candidates that pass the cheap necessary test of stage 1, again 32 at a time): the exact
 // decision and the ownership rule.  Every lane of the warp must call (the text context comes by shuffle).
 // record: x, y = index entry; z = [3:0] wi, [7:4] route, [12:8] k_probe, [17:13] lane that owns the text context
-__device__ __noinline__ void sj_stage2(int M, int t, SjText T, bool act, uint4 rec, uint32_t* __restrict__ counts) {
+__device__ __noinline__ void sj_stage2(int M, int t, bool gapless, SjText T, bool act, uint4 rec, uint32_t* __restrict__ counts) {
     const int wi = (int)(rec.z & 15u), r = (int)((rec.z >> 4) & 15u), k_probe = (int)((rec.z >> 8) & 31u), src = (int)((rec.z >> 13) & 31u);
     const uint32_t qlo = rec.x & kFull, qhi = ((rec.x >> 20) | (rec.y << 12)) & kFull, id = rec.y >> 12;
     const SjText Ts = sj_text_from(T, src);
@@ -301,7 +303,7 @@ __device__ __noinline__ void sj_stage2(int M, int t, SjText T, bool act, uint4 r
     const int o = wi + 1;
     const uint32_t D0 = sj_diag(Ts, qlo, qhi, o), DM = sj_diag(Ts, qlo, qhi, o - 1), DP = sj_diag(Ts, qlo, qhi, o + 1);
     int kq = 0;
-    const int owner = sj_canonical(D0, DM, DP, M, t, kq);
+    const int owner = sj_canonical(D0, DM, DP, M, t, gapless, kq);
     if (owner != r || (r >= 5 && kq != k_probe)) return;
     atomicAdd(counts + id, 1u);
 }
@@ -362,6 +364,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
     uint4* qs = s_surv[warp];
     const int64_t p = p_begin + ((int64_t)blockIdx.x * kSjWarps + warp) * 32 + lane;
     const int M = prm.M, t = prm.t;
+    const bool gapless = prm.gapless != 0;
     uint32_t* cnt = counts + (prm.strand > 0 ? 0 : prm.N);
     SjText T;
     T.okmask = 0u;
@@ -402,7 +405,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         st_surv += __popc(m);
         if (n_surv >= 32) {
             __syncwarp();
-            sj_stage2(M, t, T, true, qs[n_surv - 32 + lane], cnt);
+            sj_stage2(M, t, gapless, T, true, qs[n_surv - 32 + lane], cnt);
             n_surv -= 32;
             __syncwarp();
         }
@@ -424,9 +427,9 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
             // the text's 10-mer at p is H1: on the final diagonal (R2, w = p), on w - 1 (R3, w = p + 1), on w + 1 (R4, w = p - 1)
             const uint32_t d11 = sj_diag(Ts, qlo, qhi, 11), d12 = sj_diag(Ts, qlo, qhi, 12), d13 = sj_diag(Ts, qlo, qhi, 13);
             const int c1 = __popc(d12 & kH1M);
-            const bool p2 = ((ok >> 11) & 1u) && __popc(d12) <= M + 1;                           // R2 only owns ungapped alignments
-            const bool p3 = ((ok >> 12) & 1u) && c1 + __popc(d12 & d13 & kH2M) <= M;
-            const bool p4 = ((ok >> 10) & 1u) && c1 + __popc(d12 & d11 & kH2M) <= M + 1;
+            const bool p2 = ((ok >> 11) & 1u) && __popc(d12) <= (gapless ? M : M + 1);           // R2 only owns ungapped alignments
+            const bool p3 = !gapless && ((ok >> 12) & 1u) && c1 + __popc(d12 & d13 & kH2M) <= M;
+            const bool p4 = !gapless && ((ok >> 10) & 1u) && c1 + __popc(d12 & d11 & kH2M) <= M + 1;
             if (__any_sync(0xFFFFFFFFu, p2 || p3 || p4)) {
                 survive(p2, e, 11, 2, 0, src);
                 survive(p3, e, 12, 3, 0, src);
@@ -435,7 +438,8 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         } else if (cur_cls == 0) {
             // the 10-mer at p is H2 on the final diagonal (R1): w = p - 10
             const uint32_t DM = sj_diag(Ts, qlo, qhi, 1), D0 = sj_diag(Ts, qlo, qhi, 2), DP = sj_diag(Ts, qlo, qhi, 3);
-            const bool p1 = ((ok >> 1) & 1u) && min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1;
+            const bool p1 = ((ok >> 1) & 1u) && (gapless ? __popc(D0) <= M
+                                                         : min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1);
             survive(p1, e, 1, 1, 0, src);
         } else if (j == 0) {
             // a deletion before query position k of H1 (R5): H1 starts at p on w - 1, w = p + 1; the deletion must fit
@@ -588,7 +592,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         B1 = B2;
     }
     __syncwarp();
-    sj_stage2(M, t, T, lane < n_surv, lane < n_surv ? qs[lane] : make_uint4(0u, 0u, 0u, 0u), cnt);
+    sj_stage2(M, t, gapless, T, lane < n_surv, lane < n_surv ? qs[lane] : make_uint4(0u, 0u, 0u, 0u), cnt);
     if (lane == 0) { atomicAdd(stats, (unsigned long long)st_cand); atomicAdd(stats + 1, (unsigned long long)st_surv); }
 }
 
@@ -627,12 +631,18 @@ int seedjoin_stats(uint64_t* out) {
 
 // Can this screen use the seed-and-join path?  (criterion class, gRNA length, set size; MG_GAPPED=dp|seedjoin overrides the size rule)
 bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
-    if (crit->n_units != 0 || crit->max_gap != 1 || !crit->pamless || q->len != kSjL) return false;
-    if (crit->max_mismatch < 0 || crit->max_mismatch > 4 || q->n < 1 || q->n > (1 << 20)) return false;    // 20-bit gRNA index in an entry
-    const char* env = getenv("MG_GAPPED");
-    if (env && strcmp(env, "dp") == 0) return false;
-    if (env && strcmp(env, "seedjoin") == 0) return true;
-    long long min_n = 40000;                           // below this the bit-sliced DP is faster (the ~740 probes per position do not depend on N)
+    if (crit->n_units != 0 || crit->max_gap > 1 || !crit->pamless || q->len != kSjL) return false;
+    const bool gapless = crit->max_gap == 0;
+    if (crit->max_mismatch < 0 || crit->max_mismatch > (gapless ? 5 : 4)) return false;          // half-neighbourhoods of radius <= 2
+    if (q->n < 1 || q->n > (1 << 20)) return false;                                              // 20-bit gRNA index in an entry
+    const char* env = getenv("MG_SEEDJOIN");           // on | off: whatever the set size (MG_GAPPED=seedjoin | dp is the older spelling)
+    const char* old = getenv("MG_GAPPED");
+    if ((env && strcmp(env, "off") == 0) || (old && strcmp(old, "dp") == 0)) return false;
+    if ((env && strcmp(env, "on") == 0) || (old && strcmp(old, "seedjoin") == 0)) return true;
+    // Below these sizes the exhaustive kernels are faster: the probes per position (743 with a gap, 436 without) do not depend
+    // on the number of gRNA.  One B200, 135 Mb: DP 53 us, pair-word scan 9.6 us, seed-and-join ~1.5 s / N + 4.5 us (gap) or
+    // ~0.9 s / N + 1.2 us (no gap) per gRNA.
+    long long min_n = gapless ? 100000 : 40000;
     if (const char* m = getenv("MG_SEEDJOIN_MIN")) min_n = atoll(m);
     return q->n >= min_n;
 }
@@ -700,7 +710,9 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     // (the >= 64 invalid bases before the first and after the last contig make the windows at both ends of the coordinate
     // space dirty through their blocks, which is what sj_dirty assumes for wf < 3 and wf + 23 > glen)
     SjParams prm;
-    prm.N = q->n; prm.M = crit->max_mismatch; prm.t = (prm.M + 1) / 2; prm.g = prm.M - prm.t - 1;
+    prm.N = q->n; prm.M = crit->max_mismatch; prm.gapless = crit->max_gap == 0 ? 1 : 0;
+    prm.t = prm.gapless ? prm.M / 2 : (prm.M + 1) / 2;                 // a half with <= t mismatches always exists
+    prm.g = prm.gapless ? -1 : prm.M - prm.t - 1;
     prm.wb = wb; prm.we = we;
     SeedIndexView iv;
     iv.dir01 = ix->d_dir01; iv.dir23 = ix->d_dir23; iv.entries0 = ix->d_entries0; iv.entries1 = ix->d_entries1;

@@ -189,3 +189,54 @@ def test_seedjoin_default_selection_stats_and_degenerate_sets(L):
     finally:
         q.free()
         genome.free()
+
+
+@pytest.mark.parametrize("M", [5, 4, 3, 2, 1, 0])
+def test_seedjoin_ungapped_equals_pair_word_scan_and_oracle(L, M):
+    """ot_gap = 0 (Hamming <= M): routes R1 / R2 only, t = M // 2; against the pair-word scan (masks, N runs, contig ends, window
+    shards, chunk + halo genomes) and, for a subset of the gRNA, against the C oracle."""
+    from minorg_b200.ot_regex import make_criteria
+    contigs, grnas = _world(300 + M, 2500, [300000, 120000, 25, 0, 50000])
+    names = [c[0] for c in contigs]
+    masks = [(0, 1000, 3000), (0, 2500, 2600), (1, 0, 500), (4, 49000, 50000), (4, 20000, 20010)]
+    genome = L.Genome.from_contigs(contigs)
+    genome.set_masks(masks)
+    q = L.Queries(grnas)
+    crit = make_criteria(ot_mismatch=M + 1, ot_gap=0, grna_length=20)
+    try:
+        want = _counts(L, genome, q, crit, "dp")
+        got = _counts(L, genome, q, crit, "seedjoin")
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (M, bad[:10], got[bad[:10]], want[bad[:10]])
+        assert L.last_seedjoin_stats()[0] > 0
+        assert want.sum() > (20 if M else 0), M
+        glen = genome.global_length
+        cuts = [0, glen // 3 + 5, glen // 3 + 6, 2 * glen // 3, glen]
+        parts = sum(_counts(L, genome, q, crit, "seedjoin", a, b) for a, b in zip(cuts[:-1], cuts[1:]))
+        assert np.array_equal(parts, want), M
+        if M in (4, 1):
+            sub = grnas[:300]
+            q2 = L.Queries(sub)
+            ref = c_oracle.screen_hamming(contigs, masks, sub, M, threads=16).astype(np.int64)
+            c2 = _counts(L, genome, q2, crit, "seedjoin")
+            assert np.array_equal(c2[:len(sub)] + c2[len(sub):], ref), M      # the Hamming oracle reports both orientations together
+            q2.free()
+    finally:
+        q.free()
+        genome.free()
+    if M == 4:
+        blob = np.frombuffer("".join(s for _, s in contigs).encode(), dtype=np.uint8)
+        offsets = np.concatenate([[0], np.cumsum([len(s) for _, s in contigs])]).astype(np.int64)
+        q = L.Queries(grnas)
+        got = np.zeros_like(want)
+        for a, b in ((0, 200001), (200001, 300030), (300030, glen)):
+            g = L.Genome.from_host_array_chunk(blob, offsets, names, a, b, halo=256)
+            got += _counts(L, g, q, crit, "seedjoin")
+            g.free()
+        q.free()
+        # (chunk genomes carry no masks here: compare with the unmasked whole genome)
+        whole = L.Genome.from_contigs(contigs)
+        q = L.Queries(grnas)
+        assert np.array_equal(got, _counts(L, whole, q, crit, "dp"))
+        q.free()
+        whole.free()

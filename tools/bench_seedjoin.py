@@ -24,6 +24,9 @@ def main():
         i = argv.index("--frac")
         frac = float(argv[i + 1])
         del argv[i:i + 2]
+    ungapped = "--ungapped" in argv                  # Hamming <= 4 instead of <= 4 mismatches / <= 1 gap (the reference scan is then the pair-word kernel)
+    if ungapped:
+        argv.remove("--ungapped")
     counts_n = [int(x) for x in argv] or [1_000_000]
     name, sms = _lib.init(0)
     dev = torch.device("cuda", 0)
@@ -36,7 +39,7 @@ def main():
     torch.cuda.synchronize()
     found = genome.find_exact([s for _, s in targets[0]], stream=stream)
     genome.set_masks(sorted({(c, s, e) for _, c, s, e, _ in found}), stream=stream)
-    crit = make_criteria(ot_mismatch=5, ot_gap=2, grna_length=20)
+    crit = make_criteria(ot_mismatch=5, ot_gap=0 if ungapped else 2, grna_length=20)
     rng = np.random.Generator(np.random.PCG64(1000))
     total = sum(clens)
     for n in counts_n:
@@ -69,7 +72,7 @@ def main():
         t_sj_part, c_sj_part = run("seedjoin", a, b)
         t_dp_part, c_dp_part = run("dp", a, b)
         equal = bool(torch.equal(c_sj_part, c_dp_part))
-        print(json.dumps({"n_grna": n, "genome_bp": total, "criterion": "<=4 mismatches / <=1 gap, both strands, no pattern, PAM-less",
+        print(json.dumps({"n_grna": n, "genome_bp": total, "criterion": "<=4 mismatches, no gap, both strands, PAM-less (reference scan: pair-word kernel)" if ungapped else "<=4 mismatches / <=1 gap, both strands, no pattern, PAM-less",
                           "seedjoin_seconds": t_sj, "timed_fraction_of_genome": frac, "seedjoin_tcell_per_s": 2.0 * n * total / t_sj / 1e12,
                           "anchors_total": int(c_sj.sum().item()), "candidates": cand, "stage2_candidates": surv,
                           "candidates_per_cell": cand / (2.0 * n * total * min(frac, 1.0)),

@@ -110,7 +110,9 @@ def main():
                               "counts_total": int(c.astype(np.int64).sum()), "grna_failed": int(((c[:n].astype(np.int64) + c[n:]) > 0).sum()),
                               "rank0_chunk": [begin, end], "rank0_contigs_synthesised": len(need), "rank0_ascii_bytes": ascii_bytes,
                               "rank0_device_bytes": genome.device_bytes, "whole_genome_device_bytes": int(glen * 0.375),
-                              "rank0_setup_ms": setup_ms, "device": name}))
+                              "rank0_setup_ms": setup_ms, "device": name,
+                              "rank0_seedjoin_candidates": _lib.last_seedjoin_stats()[0],      # > 0: the seed-and-join screen ran (>= 10^5 gRNA)
+                              "MG_SEEDJOIN": os.environ.get("MG_SEEDJOIN", "")}))
             sys.stdout.flush()
         q.free()
     genome.free()
