@@ -241,20 +241,14 @@ __device__ __forceinline__ void sj_load32(const GenomeView& gv, int strand, int6
 // forward window start of the strand window w (20 bases from strand position w)
 __device__ __forceinline__ int64_t sj_fwd_window(const GenomeView& gv, int strand, int64_t w) { return strand > 0 ? w : gv.glen - w - kSjL; }
 
-// the window's bases [w-3, w+23) (forward) touch a 32-base block holding an invalid base
-__device__ __forceinline__ bool sj_dirty(const GenomeView& gv, int64_t wf) {
-    if (wf < 3 || wf + 23 > gv.glen) return true;
-    return (__ldg(gv.invalid + ((wf - 3) >> 5)) | __ldg(gv.invalid + ((wf + 22) >> 5))) != 0u;
-}
-
-// some masked interval meets [a, b)
-__device__ __forceinline__ bool sj_mask_near(const GenomeView& gv, int64_t a, int64_t b) {
-    int lo = 0, hi = gv.n_masks - 1, ans = -1;
+// w lies in one of the sorted, disjoint window ranges [r[2i], r[2i+1]) the host keeps for the exhaustive kernels
+__device__ __forceinline__ bool sj_delegated(const int64_t* __restrict__ r, int n, int64_t w) {
+    int lo = 0, hi = n - 1, ans = -1;
     while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
-        if (gv.mstart[mid] < b) { ans = mid; lo = mid + 1; } else hi = mid - 1;
+        if (__ldg(r + 2 * mid) <= w) { ans = mid; lo = mid + 1; } else hi = mid - 1;
     }
-    return ans >= 0 && gv.mend_pm[ans] > a;
+    return ans >= 0 && w < __ldg(r + 2 * ans + 1);
 }
 
 __device__ __forceinline__ uint32_t sj_diag(const SjText& T, uint32_t qlo, uint32_t qhi, int o) {
@@ -355,7 +349,8 @@ constexpr int kSjSurvivors = 64;                             // stage-1 survivor
 // The few per cent that pass stage 1 go to a survivor queue and are decided 32 at a time as well (sj_stage2).
 __global__ void __launch_bounds__(32 * kSjWarps, 3)
 sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_variants,
-               int64_t p_begin, int64_t p_end, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
+               int64_t p_begin, int64_t p_end, const int64_t* __restrict__ delegated, int n_delegated, uint32_t* __restrict__ counts,
+               unsigned long long* __restrict__ stats) {
     __shared__ uint32_t s_queue[kSjWarps][2][kSjQueue];
     __shared__ uint4 s_surv[kSjWarps][kSjSurvivors];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,8 +368,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
     if (p < p_end) {
         for (int wi = 0; wi <= 12; ++wi) {
             const int64_t wf = sj_fwd_window(gv, prm.strand, p - 11 + wi);
-            if (wf < prm.wb || wf >= prm.we || sj_dirty(gv, wf)) continue;
-            if (gv.n_masks && sj_mask_near(gv, wf - 3, wf + 24)) continue;
+            if (wf < prm.wb || wf >= prm.we || sj_delegated(delegated, n_delegated, wf)) continue;
             T.okmask |= 1u << wi;
         }
     }
@@ -609,6 +603,8 @@ __global__ void sj_dirty_blocks_kernel(GenomeView gv, int64_t b0, int64_t b1, un
 
 // [0] candidates (index entries compared with the text), [1] stage-1 survivors of the launches since the last reset, per device
 constexpr int kSjMaxDevices = 64;
+constexpr int64_t kSjMergeGap = 1024;                // windows
+constexpr size_t kSjMaxRanges = 4096;
 static unsigned long long* g_sj_stats[kSjMaxDevices] = {nullptr};
 
 static int sj_stats_buffer(unsigned long long** out) {
@@ -700,13 +696,24 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         // the running maximum of the ends gives the same union as the ends themselves (the interval that set it starts earlier)
         for (int i = 0; i < g->n_masks; ++i) raw.emplace_back(ms[i] - 23, me[i] + 3);
     }
+    // Merge (ranges closer than kSjMergeGap windows become one: every range is a separate launch of the exhaustive kernels, the
+    // windows in between cost them next to nothing) and clip to the call's windows.  The scan kernel skips exactly these ranges.
     std::sort(raw.begin(), raw.end());
+    int64_t n_delegated_windows = 0;
     for (const auto& r : raw) {
-        const int64_t a = std::max(wb, r.first), z = std::min(we, r.second);
-        if (a >= z) continue;
-        if (!dirty_ranges.empty() && a <= dirty_ranges.back().second) dirty_ranges.back().second = std::max(dirty_ranges.back().second, z);
-        else dirty_ranges.emplace_back(a, z);
+        if (!dirty_ranges.empty() && r.first <= dirty_ranges.back().second + kSjMergeGap) dirty_ranges.back().second = std::max(dirty_ranges.back().second, r.second);
+        else dirty_ranges.emplace_back(r.first, r.second);
     }
+    {
+        size_t k = 0;
+        for (auto& r : dirty_ranges) {
+            r.first = std::max(wb, r.first); r.second = std::min(we, r.second);
+            if (r.first < r.second) { n_delegated_windows += r.second - r.first; dirty_ranges[k++] = r; }
+        }
+        dirty_ranges.resize(k);
+    }
+    // a subject that is mostly N runs / masked intervals, or cut into very many pieces: the exhaustive kernels take all of it
+    if (dirty_ranges.size() > kSjMaxRanges || 2 * n_delegated_windows > we - wb) { dirty_ranges.clear(); return MG_ERR_UNSUPPORTED; }
     // (the >= 64 invalid bases before the first and after the last contig make the windows at both ends of the coordinate
     // space dirty through their blocks, which is what sj_dirty assumes for wf < 3 and wf + 23 > glen)
     SjParams prm;
@@ -721,21 +728,28 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     int n01 = 0;                                       // classes 0 / 1 come first
     while (n01 < (int)vars.size() && ((vars[n01] >> 20) & 3u) != 2u) ++n01;
     uint32_t* d_vars = nullptr;
+    int64_t* d_ranges = nullptr;
+    std::vector<int64_t> flat;
+    for (const auto& r : dirty_ranges) { flat.push_back(r.first); flat.push_back(r.second); }
     MG_CUDA(dev_alloc((void**)&d_vars, sizeof(uint32_t) * vars.size(), s));
+    e = dev_alloc((void**)&d_ranges, sizeof(int64_t) * std::max<size_t>(2, flat.size()), s);
+    if (e != cudaSuccess) { dev_free(d_vars, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_NOMEM; }
     e = cudaMemcpyAsync(d_vars, vars.data(), sizeof(uint32_t) * vars.size(), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);              // vars lives on this stack frame
-    if (e != cudaSuccess) { dev_free(d_vars, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    if (e == cudaSuccess && !flat.empty()) e = cudaMemcpyAsync(d_ranges, flat.data(), sizeof(int64_t) * flat.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);              // vars and flat live on this stack frame
+    if (e != cudaSuccess) { dev_free(d_vars, s); dev_free(d_ranges, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     for (int z = 0; z < 2 && e == cudaSuccess; ++z) {
         prm.strand = z == 0 ? 1 : -1;
         // strand windows of the owned forward windows, then the positions that can reach them (w - 1 .. w + 11)
         const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
-        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_counts, d_stats);
+        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
     dev_free(d_vars, s);
+    dev_free(d_ranges, s);
     if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     return MG_OK;
 }
