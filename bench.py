@@ -530,7 +530,7 @@ def main():
         out = {"metric": "gRNA x Gbp screened/sec (exhaustive, device-timed)", "value": value, "unit": "gRNA*Gbp/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bit planes of 2-bit bases)",
-               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
+               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps * world,
                "roofline": roofline, "cpu_baseline": None, "device": name, "int_peaks": int_peaks,
                "cells_per_s": 2.0 * args.grna * total_bases / (ms_per_step / 1e3), "grna_failed": fails,
                "counts_checksum": "0x%016x" % checksum, "counts_total": int(host_counts.sum()),

@@ -347,7 +347,10 @@ constexpr int kSjSurvivors = 64;                             // stage-1 survivor
 // Class 2 (tables 2 / 3, ~34 entries per bucket at 10^6 gRNA): the warp walks the buckets of one lane after the other, all
 // lanes reading consecutive entries (coalesced), the lane's context broadcast by shuffle; no queue.
 // The few per cent that pass stage 1 go to a survivor queue and are decided 32 at a time as well (sj_stage2).
-__global__ void __launch_bounds__(32 * kSjWarps, 3)
+// PHASE 0: classes 0 / 1 (queues), PHASE 1: class 2 (bucket walks) - two launches, so that each keeps only its own state in
+// registers (64 registers, 4 CTAs per SM, no spills).
+template <int PHASE>
+__global__ void __launch_bounds__(32 * kSjWarps, 4)
 sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_variants,
                int64_t p_begin, int64_t p_end, const int64_t* __restrict__ delegated, int n_delegated, uint32_t* __restrict__ counts,
                unsigned long long* __restrict__ stats) {
@@ -488,8 +491,8 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         return valid ? __ldg(ix.dir01 + key) : make_uint2(0u, 0u);
     };
 
-    uint2 Bn = dir01(0);
-    for (int v = 0; v < n01; ++v) {
+    uint2 Bn = PHASE == 0 ? dir01(0) : make_uint2(0u, 0u);
+    for (int v = 0; PHASE == 0 && v < n01; ++v) {
         const uint32_t d = __ldg(variants + v);
         const int cls = (int)((d >> 20) & 3u);
         const uint2 B = Bn;
@@ -524,8 +527,10 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
             service(J1);
         } while (__any_sync(0xFFFFFFFFu, (n0 | n1) != 0u));
     }
-    flush(J0);
-    flush(J1);
+    if (PHASE == 0) {
+        flush(J0);
+        flush(J1);
+    }
 
     // class 2: the text's 9-mer at p is H1 without its position ke (R6: an insertion at query position ke, H1 starts at p on
     // w + 1, w = p - 1) or H2 without its position ke (R8: insertion at 10 + ke, w + 1 = p - 10); the insertion must fit
@@ -537,7 +542,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
     // while one is evaluated.
     struct Item { int src; uint32_t base, n2, nn; uint2 e; };
     int v2 = n01 - 1;                                               // generator state (warp-uniform but for C)
-    uint2 C = make_uint2(0u, 0u), Cn = dir23(n01);
+    uint2 C = make_uint2(0u, 0u), Cn = PHASE == 1 ? dir23(n01) : make_uint2(0u, 0u);
     unsigned todo = 0u;
     int g_src = -1;
     uint32_t g_base = 0u, g_a = 0u, g_n2 = 0u, g_nn = 0u;
@@ -576,9 +581,12 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         survive(pass, it.e, wi, t3 ? 8 : 6, kp, it.src);
     };
     Item A, B1, B2;
-    next(A);
-    next(B1);
-    while (A.src >= 0) {
+    A.src = B1.src = -1;
+    if (PHASE == 1) {
+        next(A);
+        next(B1);
+    }
+    while (PHASE == 1 && A.src >= 0) {
         B2.src = -1;
         if (B1.src >= 0) next(B2);
         process(A);
@@ -744,7 +752,10 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         const int64_t ws0 = z == 0 ? wb : g->glen - we - kSjL + 1, ws1 = z == 0 ? we : g->glen - wb - kSjL + 1;
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
-        sj_scan_kernel<<<(unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps)), 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+        const unsigned grid = (unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps));
+        sj_scan_kernel<0><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+        if (n01 < (int)vars.size())
+            sj_scan_kernel<1><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
