@@ -335,6 +335,9 @@ constexpr int kSjWarps = 8;                                  // warps per CTA
 constexpr int kSjQueue = 160;                                // candidate records per warp and queue (4 B each): < 32 left over + 32 lanes x kSjRound
 constexpr int kSjRound = 4;                                  // records a lane may append per table and round
 constexpr int kSjSurvivors = 64;                             // stage-1 survivors per warp (16 B each): < 32 left over + 32
+constexpr int kSjItemsPerLane = 4;                           // class 2: items (32 entries) a lane lists per round
+constexpr int kSjItems = 32 * kSjItemsPerLane;               // list capacity per warp
+
 
 // One warp = 32 consecutive text positions, one lane each; the context of a position (64 bases as bit planes) stays in its
 // lane's registers and travels by shuffle.
@@ -354,11 +357,13 @@ __global__ void __launch_bounds__(32 * kSjWarps, 4)
 sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_variants,
                int64_t p_begin, int64_t p_end, const int64_t* __restrict__ delegated, int n_delegated, uint32_t* __restrict__ counts,
                unsigned long long* __restrict__ stats) {
-    __shared__ uint32_t s_queue[kSjWarps][2][kSjQueue];
+    // PHASE 0: two queues of 4-byte records; PHASE 1: the item list and the cp.async ring
+    constexpr int kBufBytes = PHASE == 0 ? 2 * kSjQueue * 4 : kSjItems * 16 + 4 * 32 * 8;
+    __shared__ __align__(16) unsigned char s_buf[kSjWarps][kBufBytes];
     __shared__ uint4 s_surv[kSjWarps][kSjSurvivors];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* q0 = s_queue[warp][0];
-    uint32_t* q1 = s_queue[warp][1];
+    uint32_t* q0 = reinterpret_cast<uint32_t*>(s_buf[warp]);
+    uint32_t* q1 = q0 + kSjQueue;
     uint4* qs = s_surv[warp];
     const int64_t p = p_begin + ((int64_t)blockIdx.x * kSjWarps + warp) * 32 + lane;
     const int M = prm.M, t = prm.t;
@@ -538,60 +543,68 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         if (v >= n_variants || !live) return make_uint2(0u, 0u);
         return __ldg(ix.dir23 + (S9 ^ (__ldg(variants + v) & kFull)));
     };
-    // Work items = (lane whose bucket is walked, 32 consecutive entries of it); the entries of the next two items are in flight
-    // while one is evaluated.
-    struct Item { int src; uint32_t base, n2, nn; uint2 e; };
-    int v2 = n01 - 1;                                               // generator state (warp-uniform but for C)
-    uint2 C = make_uint2(0u, 0u), Cn = PHASE == 1 ? dir23(n01) : make_uint2(0u, 0u);
-    unsigned todo = 0u;
-    int g_src = -1;
-    uint32_t g_base = 0u, g_a = 0u, g_n2 = 0u, g_nn = 0u;
-    auto next = [&](Item& it) {
-        it.src = -1;
-        if (g_src >= 0 && g_base + 32u < g_nn) {
-            g_base += 32u;
-        } else {
-            while (todo == 0u) {                                    // next variant with a non-empty bucket
-                if (++v2 >= n_variants) { g_src = -1; return; }
-                C = Cn;
-                Cn = dir23(v2 + 1);
-                todo = __ballot_sync(0xFFFFFFFFu, C.y != 0u);
-            }
-            g_src = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const uint32_t by = __shfl_sync(0xFFFFFFFFu, C.y, g_src);
-            g_a = __shfl_sync(0xFFFFFFFFu, C.x, g_src); g_n2 = by & 0xFFFFu; g_nn = g_n2 + (by >> 16);
-            g_base = 0u;
-            st_cand += g_nn;
-        }
-        const uint32_t i = g_base + lane;
-        it.src = g_src; it.base = g_base; it.n2 = g_n2; it.nn = g_nn;
-        it.e = i < g_nn ? __ldg(ix.entries23 + g_a + i) : make_uint2(0u, 0u);
-    };
-    int t_src = -1;
-    SjText Ts = T;
-    auto process = [&](const Item& it) {
-        if (it.src != t_src) { Ts = sj_text_from(T, it.src); t_src = it.src; }
-        const uint32_t i = it.base + lane;
-        const bool t3 = i >= it.n2;
-        const int ke = (int)((it.e.y >> 8) & 15u), wi = t3 ? 0 : 10, kp = t3 ? 10 + ke : ke;
-        const uint32_t qlo = it.e.x & kFull, qhi = ((it.e.x >> 20) | (it.e.y << 12)) & kFull, lowk = (1u << kp) - 1u;
-        const bool pass = i < it.nn && ((Ts.okmask >> wi) & 1u) &&
-                          __popc(sj_diag(Ts, qlo, qhi, wi + 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, wi + 1) & ~(2u * lowk + 1u)) <= M;
-        survive(pass, it.e, wi, t3 ? 8 : 6, kp, it.src);
-    };
-    Item A, B1, B2;
-    A.src = B1.src = -1;
+    // Work items = (lane whose bucket is walked, 32 consecutive entries of it).  Per variant the lanes write their items into a
+    // list in shared memory (one scan); the warp then runs down the list, all lanes reading consecutive entries (coalesced).
+    // The entries travel global -> shared by cp.async three items ahead, each lane reading back only its own slot, so no
+    // register is tied up by a load in flight and nothing has to be rotated.
     if (PHASE == 1) {
-        next(A);
-        next(B1);
-    }
-    while (PHASE == 1 && A.src >= 0) {
-        B2.src = -1;
-        if (B1.src >= 0) next(B2);
-        process(A);
-        A = B1;
-        B1 = B2;
+        uint4* items = reinterpret_cast<uint4*>(q0);                // kSjItems x 16 B: x = first entry, y = n2 | nn << 16, z = lane | base << 8
+        uint2* ring = reinterpret_cast<uint2*>(items + kSjItems);   // 4 slots x 32 lanes
+        uint2 Cn = dir23(n01);
+        int t_src = -1;
+        SjText Ts = T;
+        for (int v = n01; v < n_variants; ++v) {
+            const uint2 C = Cn;
+            Cn = dir23(v + 1);
+            uint32_t done = 0u;                                     // entries of this lane's bucket already listed
+            const uint32_t n2 = C.y & 0xFFFFu, nn = n2 + (C.y >> 16);
+            for (;;) {
+                // every lane lists up to kSjItemsPerLane items of its bucket per round
+                const uint32_t left = nn - done;
+                const int c = (int)min((uint32_t)kSjItemsPerLane, (left + 31u) >> 5);
+                int off = c;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, off, dd); if (lane >= dd) off += o; }
+                const int n_items = __shfl_sync(0xFFFFFFFFu, off, 31);
+                if (n_items == 0) break;
+                off -= c;
+#pragma unroll
+                for (int j = 0; j < kSjItemsPerLane; ++j)
+                    if (j < c) items[off + j] = make_uint4(C.x, C.y, (uint32_t)lane | ((done + 32u * j) << 8), 0u);
+                done += 32u * c;
+                st_cand += __reduce_add_sync(0xFFFFFFFFu, min(left, 32u * c));
+                __syncwarp();
+                auto issue = [&](int it) {
+                    if (it < n_items) {
+                        const uint4 d = items[it];
+                        const uint32_t i = (d.z >> 8) + lane;
+                        if (i < (d.y & 0xFFFFu) + (d.y >> 16)) {
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (it & 3) * 32 + lane);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(ix.entries23 + d.x + i) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                issue(0); issue(1); issue(2);
+                for (int it = 0; it < n_items; ++it) {
+                    asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    const uint4 d = items[it];
+                    const uint2 e = ring[(it & 3) * 32 + lane];
+                    const int src = (int)(d.z & 31u);
+                    if (src != t_src) { Ts = sj_text_from(T, src); t_src = src; }
+                    const uint32_t i = (d.z >> 8) + lane, in2 = d.y & 0xFFFFu, inn = in2 + (d.y >> 16);
+                    const bool t3 = i >= in2;
+                    const int ke = (int)((e.y >> 8) & 15u), wi = t3 ? 0 : 10, kp = t3 ? 10 + ke : ke;
+                    const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull, lowk = (1u << kp) - 1u;
+                    const bool pass = i < inn && ((Ts.okmask >> wi) & 1u) &&
+                                      __popc(sj_diag(Ts, qlo, qhi, wi + 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, wi + 1) & ~(2u * lowk + 1u)) <= M;
+                    survive(pass, e, wi, t3 ? 8 : 6, kp, src);
+                    issue(it + 3);                                   // slot (it + 3) & 3 was read one item ago
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+        }
     }
     __syncwarp();
     sj_stage2(M, t, gapless, T, lane < n_surv, lane < n_surv ? qs[lane] : make_uint4(0u, 0u, 0u, 0u), cnt);
