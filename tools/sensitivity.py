@@ -127,7 +127,98 @@ def run(label, ascii_host, grnas, mask_seqs, note):
     genome.free()
 
 
+def run_seedjoin(label, ascii_host, grnas, mask_seqs, note):
+    """The north-star criterion (<= 4 mismatches / <= 1 gap) through the seed-and-join screen on the same kinds of genome, with
+    a gRNA set large enough for it (skewed sets fill some index buckets much more than a random set does); the DP path on 1/64
+    of the windows for comparison, per-gRNA counts compared on that range."""
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    clen = GENOME_BP // CONTIGS
+    offsets = np.arange(CONTIGS + 1, dtype=np.int64) * clen
+    d = torch.from_numpy(np.ascontiguousarray(ascii_host[:clen * CONTIGS])).to(dev)
+    genome = _lib.Genome.from_device_ascii(d.data_ptr(), offsets, ["c%d" % i for i in range(CONTIGS)], stream=stream)
+    torch.cuda.synchronize()
+    del d
+    masks = sorted({(c, s, e) for _, c, s, e, _ in genome.find_exact(mask_seqs, stream=stream)}) if mask_seqs else []
+    genome.set_masks(masks, stream=stream)
+    q = _lib.Queries(grnas, stream=stream)
+    n = len(grnas)
+    crit = make_criteria(ot_mismatch=5, ot_gap=2, grna_length=L)
+    counts = torch.zeros(2 * n, dtype=torch.int32, device=dev)
+    glen = genome.global_length
+
+    def timed(mode, wb=0, we=-1):
+        os.environ["MG_SEEDJOIN"] = mode
+        counts.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.screen(genome, q, crit, None, counts.data_ptr(), win_begin=wb, win_end=we, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3, counts.clone()
+    timed("on", 0, 1 << 20)                                        # index build, warm-up
+    sec, c_all = timed("on")
+    cand, surv = _lib.last_seedjoin_stats()
+    a, b = glen // 2, glen // 2 + glen // 64
+    t_sj, c_sj = timed("on", a, b)
+    t_dp, c_dp = timed("off", a, b)
+    os.environ.pop("MG_SEEDJOIN", None)
+    c = c_all.cpu().numpy().astype(np.int64)
+    print(json.dumps({"genome": label, "criterion": "<=4 mismatches / <=1 gap, seed-and-join screen", "note": note, "genome_bp": clen * CONTIGS,
+                      "n_grna": n, "masks": len(masks), "seconds": sec, "tcell_per_s": 2.0 * n * clen * CONTIGS / sec / 1e12,
+                      "seedjoin_path_ran": cand > 0, "candidates_per_cell": cand / (2.0 * n * clen * CONTIGS), "stage2_fraction": surv / max(1, cand),
+                      "anchors_total": int(c.sum()), "grna_failed": int(((c[:n] + c[n:]) > 0).sum()),
+                      "range_windows": b - a, "seedjoin_seconds_on_range": t_sj, "dp_seconds_on_range": t_dp,
+                      "counts_equal_on_range": bool(torch.equal(c_sj, c_dp))}))
+    sys.stdout.flush()
+    q.free()
+    genome.free()
+
+
+def top_up(rng, grnas, n, p=None):
+    """Fill a gRNA list to n with point variants of its members (half of the rest) and random 20-mers of base composition p."""
+    seen, out = set(grnas), list(grnas)
+    base_n = len(out)
+    while len(out) < n:
+        if base_n and len(out) < base_n + (n - base_n) // 2:
+            k = list(out[int(rng.integers(0, base_n))])
+            for _ in range(int(rng.integers(1, 4))):
+                k[int(rng.integers(0, L))] = "ACGT"[int(rng.integers(0, 4))]
+            k = "".join(k)
+        else:
+            k = LUT[rng.choice(4, size=L, p=p)].tobytes().decode()
+        if k not in seen:
+            seen.add(k)
+            out.append(k)
+    return out
+
+
+def main_seedjoin(n_grna):
+    _lib.init(0)
+    rng = np.random.Generator(np.random.PCG64(43))
+    g, targets = genome_uniform(rng)
+    seqs = [LUT[t].tobytes().decode() for t in targets]
+    for i, t in enumerate(targets):
+        g[1_000_000 * (i + 1):1_000_000 * (i + 1) + len(t)] = t
+    run_seedjoin("uniform", LUT[g], top_up(rng, enumerate_grnas(seqs, n_grna), n_grna), seqs,
+                 "i.i.d. uniform ACGT; gRNA from 40 planted random 2-kb targets (masked), their point variants and random 20-mers")
+    g, family = genome_at_rich(rng)
+    seqs = [LUT[t].tobytes().decode() for t in family]
+    for i, t in enumerate(family):
+        g[10_000_000 * (i + 1):10_000_000 * (i + 1) + len(t)] = t
+    run_seedjoin("at_rich_repeats_gene_family", LUT[g], top_up(rng, enumerate_grnas(seqs, n_grna), n_grna, p=[0.32, 0.18, 0.18, 0.32]), seqs,
+                 "36 % GC, 5 % tandem + dispersed repeats; gRNA from a planted 10-member gene family at ~90 % identity (members masked), 1-3-base "
+                 "variants of them (half of the set: thousands of gRNA share their halves) and random 20-mers of the genome's composition")
+    g, tseqs, unit = genome_tiled()
+    parts = [bytes(g[i:i + 200_000]).decode("latin-1") for i in range(0, unit, 200_000)]
+    run_seedjoin("config1_tiled", g, top_up(rng, enumerate_grnas(tseqs + parts, n_grna), n_grna), tseqs,
+                 "bundled config-1 genomes (%d bp) tiled %.0fx to 135 Mb; gRNA = NGG sites of the target genes and of the genomes themselves "
+                 "(every hit repeats ~134x), variants, random" % (unit, GENOME_BP / unit))
+
+
 def main():
+    if "--seedjoin" in sys.argv:
+        return main_seedjoin(int(sys.argv[sys.argv.index("--seedjoin") + 1]) if len(sys.argv) > sys.argv.index("--seedjoin") + 1 else 200_000)
     _lib.init(0)
     rng = np.random.Generator(np.random.PCG64(42))
     g, targets = genome_uniform(rng)
