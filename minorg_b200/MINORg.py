@@ -22,6 +22,8 @@ from .minimum_set import minimum_sets
 from .ot_regex import MINORgError, OffTargetExpression, make_criteria
 from .pam import PAM
 
+_MAX_QUERIES = 1 << 20      # gRNA per query handle (the seed-and-join index addresses 2^20; larger sets are screened in parts)
+
 
 class Masked:
     """A masked (on-target) interval: 0-based, end-exclusive (filter_grna.py:44-65)."""
@@ -360,11 +362,14 @@ class MINORg:
             for end in cuts:
                 if end <= begin or not alive:
                     continue
-                q = _lib.Queries([seqs[i] for i in alive], stream=stream)
-                c = _lib.screen_counts(genome, q, crit, pam, win_begin=begin, win_end=end, stream=stream).astype(np.int64)
-                c = c[:len(alive)] + c[len(alive):]
+                c = np.zeros(len(alive), dtype=np.int64)
+                for j in range(0, len(alive), _MAX_QUERIES):      # one query handle indexes at most 2^20 gRNA for the seed-and-join screen
+                    part = alive[j:j + _MAX_QUERIES]
+                    q = _lib.Queries([seqs[i] for i in part], stream=stream)
+                    cp = _lib.screen_counts(genome, q, crit, pam, win_begin=begin, win_end=end, stream=stream).astype(np.int64)
+                    c[j:j + len(part)] = cp[:len(part)] + cp[len(part):]
+                    q.free()
                 out[alive] += c
-                q.free()
                 if self.screen_verdicts_only:
                     alive = [i for i, x in zip(alive, c) if x == 0]
                 begin = end

@@ -188,3 +188,50 @@ def test_class_rejects_device_limits_by_name(tmp_path):
         m._criteria(20)
     m.ot_gap = 4
     m._criteria(20)
+
+
+def test_large_grna_set_takes_the_seed_and_join_screen_with_the_same_verdicts(tmp_path):
+    """grna() on a 700-kb target gives > 40 000 gRNA: filter_background with the one-gap criterion then runs the seed-and-join
+    screen by itself (mg_last_seedjoin_stats > 0); the verdicts equal those of the exhaustive DP path (MG_SEEDJOIN=off)."""
+    import random
+    from minorg_b200 import _lib
+    from minorg_b200.MINORg import MINORg
+    rng = random.Random(77)
+    target = "".join(rng.choice("ACGT") for _ in range(700000))
+    chrom = [rng.choice("ACGT") for _ in range(1500000)]
+    for _ in range(300):                                  # diverged copies of target pieces: off-targets with mismatches and gaps
+        a = rng.randrange(0, len(target) - 400)
+        piece = list(target[a:a + 400])
+        for _ in range(rng.randrange(5, 40)):
+            j = rng.randrange(len(piece))
+            r = rng.random()
+            if r < 0.6:
+                piece[j] = rng.choice("ACGT")
+            elif r < 0.8:
+                del piece[j]
+            else:
+                piece.insert(j, rng.choice("ACGT"))
+        b = rng.randrange(0, len(chrom) - 500)
+        chrom[b:b + len(piece)] = piece
+    (tmp_path / "t.fasta").write_text(">gene\n%s\n" % target)
+    (tmp_path / "bg.fasta").write_text(">chr1\n%s\n>chr2\n%s\n" % ("".join(chrom), target[:300000]))
+    verdicts, ran = [], []
+    for mode in ("", "off"):
+        if mode:
+            os.environ["MG_SEEDJOIN"] = mode
+        try:
+            m = MINORg(directory=str(tmp_path / ("run" + mode)), prefix="big")
+            m.target = str(tmp_path / "t.fasta")
+            m.add_background(str(tmp_path / "bg.fasta"), alias="bg")
+            m.ot_mismatch, m.ot_gap = 3, 2
+            m.grna()
+            assert len(m.grna_hits.seqs) > 40000
+            m.filter_background()
+            ran.append(_lib.last_seedjoin_stats()[0] > 0)
+            verdicts.append([m.grna_hits.get_gRNAseq_by_seq(s).check("background") for s in m.grna_hits.seqs])
+            m.close()
+        finally:
+            os.environ.pop("MG_SEEDJOIN", None)
+    assert ran[0]
+    assert verdicts[0] == verdicts[1]
+    assert 100 < sum(v is False for v in verdicts[0]) < len(verdicts[0])
