@@ -1,6 +1,7 @@
-// K7: seed-and-join screen for the no-pattern ONE-GAP criterion on LARGE gRNA sets (the north star's job: 10^6 gRNA,
-// <= 4 mismatches / <= 1 gap).  Replaces, for that criterion, the bit-sliced edit-distance DP of screen_gapped.cu, which has
-// to touch every (gRNA, text position, DP row): 182 issue slots per 32 cells whatever the data.
+// K7: seed-and-join screen for the no-pattern criteria with AT MOST ONE GAP on LARGE gRNA sets (the north star's job: 10^6
+// gRNA, <= 4 mismatches / <= 1 gap; also plain Hamming <= M, see "Without gaps" below).  Replaces, for those criteria, the
+// bit-sliced edit-distance DP of screen_gapped.cu, which has to touch every (gRNA, text position, DP row): 182 issue slots per
+// 32 cells whatever the data - and, for sets of >= 10^5 gRNA, the pair-word scan of screen_bitsliced.cu.
 //
 // Criterion (MINORg.py:2018-2044 with ot_gap = 2, no pattern, PAM-less): an anchor (gRNA, strand, virtual end e) is
 // problematic iff some alignment ending there has  mm <= M, gaps <= 1, mm + gaps + unaligned <= M + 1.  For a window whose
@@ -16,13 +17,15 @@
 //     R3  H1 on w-1 (a deletion follows)        with <= t                 R4  H1 on w+1 (an insertion follows) with <= t
 //     R5  H1 with a deletion before k = 1..9    and <= g mismatches       R6  H1 with an insertion at k = 1..9, <= g
 //     R7  H2 with a deletion before k = 11..19  and <= g                  R8  H2 with an insertion at k = 10..18, <= g
-// So instead of asking every gRNA about every position, every text position asks two hash tables (gRNA by H1, gRNA by H2,
-// direct-addressed by the 20-bit 10-mer) for the gRNA whose half equals one of the strings the text can produce: the
-// Hamming-<=t neighbours of the 10-mer at p (R1-R4), the 11-mer at p with one inner base removed and <= g substitutions
-// (R5, R7), the 9-mer at p with one base inserted and <= g substitutions (R6, R8): ~1 800 keys per position and strand,
-// independent of the number of gRNA; at 10^6 gRNA ~0.95 candidates per key, i.e. 3.5e-3 of the cells are looked at, each
-// with ~25 instructions (three diagonal mismatch masks from bit planes held in registers, one route-specific necessary
-// test), and ~4 % of those with the exact evaluation above.
+// So instead of asking every gRNA about every position, every text position asks hash tables of the gRNA SET (by H1, by H2,
+// direct-addressed by the 20-bit 10-mer; by H1 / H2 without one of their positions, 18-bit 9-mer) for the gRNA whose half
+// equals one of the strings the text can produce: the Hamming-<=t neighbours of the 10-mer at p (R1-R4: 436 strings for
+// t = 2), the 11-mer at p with one inner base removed and <= g substitutions (R5, R7: 279), the 9-mer at p with <= g
+// substitutions against the tables that lack a position (R6, R8: 28 - the index, not the text, enumerates the inserted base):
+// 743 directory probes per position and strand, independent of the number of gRNA; at 10^6 gRNA ~0.95 entries per 10-mer
+// bucket and ~34 per 9-mer bucket, i.e. 3.15e-3 of the cells are looked at (counted by the kernel: mg_last_seedjoin_stats),
+// each with ~30 instructions (two or three diagonal mismatch masks from bit planes held in registers, one route-specific
+// necessary test), and 4.2 % of those with the exact evaluation above.
 //
 // Exactly-once counting.  An anchor can be reached through several routes and variants (from different threads).  It is
 // counted by the route that its CANONICAL alignment (ungapped if it fits, else the deletion with the smallest k, else the
@@ -31,9 +34,14 @@
 //
 // Dirty windows.  A window whose bases [w-3, w+23) touch a 32-base block with an invalid base (N, IUPAC, contig padding,
 // i.e. also everything that hangs off a contig end), or whose bases [w-3, w+24) meet a masked (on-target) interval - there
-// "problematic" also depends on spans - is left to the DP path and its exact verifier: the host collects those blocks and
-// the intervals, merges them into window ranges and runs the prefilter + verifier on them.  Both paths use the same
-// predicates, so every anchor is owned by exactly one of them.
+// "problematic" also depends on spans - is left to the exhaustive kernels (DP prefilter + exact verifier; pair-word scan without
+// gaps): the host collects those blocks and the intervals, merges them into window ranges (launch_seedjoin), hands the ranges
+// to the scan kernel, which skips exactly those windows, and to the caller, which screens them.  Every anchor is owned by
+// exactly one side.
+//
+// Without gaps (crit->max_gap == 0, Hamming <= M <= 5): routes R1 / R2 only, t = floor(M/2), stage 1 is the exact test.
+//
+// tests/test_seedjoin_logic.py restates this scheme in Python and checks it against the exhaustive C oracle on the CPU.
 #include <algorithm>
 #include <type_traits>
 #include <vector>
