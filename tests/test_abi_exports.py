@@ -53,3 +53,18 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "screen_oracle" not in src, f
+
+
+def test_shipped_library_matches_the_sources():
+    """build() rebuilds by CONTENT (a SHA-256 of source + headers + flags next to every object): after it, the library's recorded
+    digest is the digest of the tree, and a second call compiles nothing."""
+    import time
+    from minorg_b200 import build
+    lib_path = build.build()
+    d = build.source_digest()
+    assert d is not None and len(d) == 64
+    before = os.path.getmtime(lib_path)
+    t0 = time.time()
+    build.build()
+    assert os.path.getmtime(lib_path) == before and time.time() - t0 < 5.0
+    assert build.source_digest() == d
