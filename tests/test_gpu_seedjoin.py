@@ -240,3 +240,46 @@ def test_seedjoin_ungapped_equals_pair_word_scan_and_oracle(L, M):
         assert np.array_equal(got, _counts(L, whole, q, crit, "dp"))
         q.free()
         whole.free()
+
+
+def test_seedjoin_ragged_subjects_fall_back_or_delegate(L):
+    """Subjects that are mostly N runs, cut into thousands of short contigs, or carry thousands of masked intervals: the
+    delegated window ranges exceed their share / count limits and the exhaustive kernels take the whole call (the seed-and-join
+    counters read zero), or - below the limits - the two sides split the windows.  Counts are the DP path's."""
+    import torch
+    from minorg_b200.ot_regex import make_criteria
+    rng = random.Random(31)
+    crit = make_criteria(ot_mismatch=5, ot_gap=2, grna_length=20)
+    base = _contig(rng, 120000)
+    grnas = []
+    for i in range(600):
+        p = rng.randrange(0, len(base) - 30)
+        g = list(base[p:p + 20])
+        for _ in range(rng.choice([0, 1, 2, 3, 4])):
+            g[rng.randrange(20)] = rng.choice("ACGT")
+        grnas.append("".join(g))
+    q = L.Queries(grnas)
+    try:
+        # (1) an N every ~40 bases: every window is near an invalid block
+        s = list(base)
+        for j in range(0, len(s), 41):
+            s[j] = "N"
+        # (2) 3 000 contigs of 40 bases; (3) 6 000 masked intervals of 5 bases, 20 apart
+        cases = [([("a", "".join(s))], []),
+                 ([("c%d" % i, base[40 * i:40 * i + 40]) for i in range(3000)], []),
+                 ([("a", base)], [(0, 20 * i, 20 * i + 5) for i in range(6000)]),
+                 ([("a", base)], [(0, 3000 * i, 3000 * i + 400) for i in range(40)])]
+        for k, (contigs, masks) in enumerate(cases):
+            genome = L.Genome.from_contigs(contigs)
+            genome.set_masks(masks)
+            want = _counts(L, genome, q, crit, "dp")
+            got = _counts(L, genome, q, crit, "seedjoin")
+            assert np.array_equal(got, want), k
+            if k < 3:
+                assert L.last_seedjoin_stats() == (0, 0), k        # the scan kernel did not run
+            else:
+                assert L.last_seedjoin_stats()[0] > 0
+            genome.free()
+        assert want.sum() > 100
+    finally:
+        q.free()
