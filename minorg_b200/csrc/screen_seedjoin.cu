@@ -43,6 +43,7 @@
 //
 // tests/test_seedjoin_logic.py restates this scheme in Python and checks it against the exhaustive C oracle on the CPU.
 #include <algorithm>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -513,6 +514,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         if (cls != cur_cls) { flush(J0); flush(J1); cur_cls = cls; }   // a queue only ever holds one route family
         if (pend0) eval(J0);
         if (pend1) eval(J1);
+        if (!__any_sync(0xFFFFFFFFu, (B.x | B.y) != 0u)) continue;  // no lane found anything: the common case for small gRNA sets
         const uint32_t tag = ((uint32_t)lane << 20) | (((d >> 22) & 15u) << 25);
         uint32_t a0 = B.x >> kSjCountBits01, n0 = B.x & ((1u << kSjCountBits01) - 1u);
         uint32_t a1 = B.y >> kSjCountBits01, n1 = B.y & ((1u << kSjCountBits01) - 1u);
@@ -667,7 +669,7 @@ bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
     // Below these sizes the exhaustive kernels are faster: the probes per position (743 with a gap, 436 without) do not depend
     // on the number of gRNA.  One B200, 135 Mb: DP 53 us, pair-word scan 9.6 us, seed-and-join ~1.5 s / N + 4.5 us (gap) or
     // ~0.9 s / N + 1.2 us (no gap) per gRNA.
-    long long min_n = gapless ? 100000 : 40000;
+    long long min_n = gapless ? 100000 : 30000;
     if (const char* m = getenv("MG_SEEDJOIN_MIN")) min_n = atoll(m);
     return q->n >= min_n;
 }
@@ -677,11 +679,16 @@ bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
 int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const GeneralCtx* d_ctx, int64_t wb, int64_t we,
                     uint32_t* d_counts, cudaStream_t s, std::vector<std::pair<int64_t, int64_t>>& dirty_ranges) {
     dirty_ranges.clear();
-    if (q->sj == nullptr) {
-        SeedIndex* ix = nullptr;
-        const int rc = seed_index_build(q, s, &ix);
-        q->sj = ix;
-        if (rc != MG_OK) return rc;
+    {
+        // built once per query handle, whichever thread screens with it first
+        static std::mutex build_lock;
+        std::lock_guard<std::mutex> guard(build_lock);
+        if (q->sj == nullptr) {
+            SeedIndex* ix = nullptr;
+            const int rc = seed_index_build(q, s, &ix);
+            if (rc != MG_OK) { seed_index_free(ix); return rc; }
+            q->sj = ix;
+        }
     }
     const SeedIndex* ix = q->sj;
     if (!ix->usable) return MG_ERR_UNSUPPORTED;
