@@ -195,7 +195,7 @@ typedef struct {
  * pam may be NULL when crit->pamless.
  * Algorithm by criterion (same counts whichever runs): no gap -> bit-sliced pair-word scan; gaps or a pattern -> a prefilter
  * (bit-sliced edit distance, or exact pieces) + the exact verifier; no pattern, <= 1 gap, <= 4 mismatches (<= 5 without gap),
- * PAM-less, 20-nt gRNA and a large set (>= 30 000 gRNA with a gap, >= 100 000 without; environment MG_SEEDJOIN_MIN, and
+ * PAM-less, 20-nt gRNA and a large set (>= 25 000 gRNA with a gap, >= 100 000 without; environment MG_SEEDJOIN_MIN, and
  * MG_SEEDJOIN=off|on forces either) -> the seed-and-join screen, which builds a hash index of the gRNA set on first use and
  * keeps it in the mg_queries handle (~170 B per gRNA). */
 int mg_screen(const mg_genome* g, const mg_queries* q, const mg_criteria* crit, const mg_pam* pam,

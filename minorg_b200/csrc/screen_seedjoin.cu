@@ -361,9 +361,10 @@ constexpr int kSjItems = 32 * kSjItemsPerLane;               // list capacity pe
 // The few per cent that pass stage 1 go to a survivor queue and are decided 32 at a time as well (sj_stage2).
 // PHASE 0: classes 0 / 1 (queues), PHASE 1: class 2 (bucket walks) - two launches, so that each keeps only its own state in
 // registers (64 registers, 4 CTAs per SM, no spills).
-template <int PHASE>
+// Q2 (phase 0 only): class 2 goes through the queues as well (short 9-mer buckets: gRNA sets below kSjWalkMinN).
+template <int PHASE, bool Q2>
 __global__ void __launch_bounds__(32 * kSjWarps, 4)
-sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_variants,
+sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __restrict__ variants, int n01, int n_queued, int n_variants,
                int64_t p_begin, int64_t p_end, const int64_t* __restrict__ delegated, int n_delegated, uint32_t* __restrict__ counts,
                unsigned long long* __restrict__ stats) {
     // PHASE 0: two queues of 4-byte records; PHASE 1: the item list and the cp.async ring
@@ -430,7 +431,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         const bool act = lane < (j ? pend1 : pend0);
         const uint32_t rec = j ? prec1 : prec0;
         const uint2 e = j ? pent1 : pent0;
-        const int src = (int)((rec >> 20) & 31u), kv = (int)((rec >> 25) & 15u);
+        const int src = (int)(rec >> 27), kv = (int)((rec >> 20) & 15u);
         const SjText Ts = sj_text_from(T, src);
         const uint32_t ok = act ? Ts.okmask : 0u;
         const uint32_t qlo = e.x & kFull, qhi = ((e.x >> 20) | (e.y << 12)) & kFull;
@@ -452,6 +453,13 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
             const bool p1 = ((ok >> 1) & 1u) && (gapless ? __popc(D0) <= M
                                                          : min(__popc(DM & D0 & kH1M), __popc(DP & D0 & kH1M)) + __popc(D0 & kH2M) <= M + 1);
             survive(p1, e, 1, 1, 0, src);
+        } else if (Q2 && cur_cls == 2) {
+            // the 9-mer at p is H1 without its position ke (R6: w = p - 1) or H2 without its position ke (R8: w + 1 = p - 10), see
+            // the bucket walk below; here for short buckets (small gRNA sets)
+            const int ke = (int)((e.y >> 8) & 15u), wi = j ? 0 : 10, kp = j ? 10 + ke : ke;
+            const uint32_t lowk = (1u << kp) - 1u;
+            const bool p68 = ((ok >> wi) & 1u) && __popc(sj_diag(Ts, qlo, qhi, wi + 2) & lowk) + __popc(sj_diag(Ts, qlo, qhi, wi + 1) & ~(2u * lowk + 1u)) <= M;
+            survive(p68, e, wi, j ? 8 : 6, kp, src);
         } else if (j == 0) {
             // a deletion before query position k of H1 (R5): H1 starts at p on w - 1, w = p + 1; the deletion must fit
             const uint32_t lowk = (1u << kv) - 1u;
@@ -471,7 +479,8 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         int& qlen = j ? qlen1 : qlen0;
         const int take = qlen < 32 ? qlen : 32;
         const uint32_t rec = lane < take ? (j ? q1 : q0)[qlen - take + lane] : 0u;
-        const uint2 e = lane < take ? __ldg((j ? ix.entries1 : ix.entries0) + (rec & kFull)) : make_uint2(0u, 0u);
+        const uint2* table = Q2 && cur_cls == 2 ? ix.entries23 : (j ? ix.entries1 : ix.entries0);
+        const uint2 e = lane < take ? __ldg(table + (rec & (Q2 && cur_cls == 2 ? 0x7FFFFFFu : kFull))) : make_uint2(0u, 0u);
         if (j) { prec1 = rec; pent1 = e; pend1 = take; } else { prec0 = rec; pent0 = e; pend0 = take; }
         qlen -= take;
         __syncwarp();
@@ -489,9 +498,12 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
 
     // directory words of variant v (classes 0 / 1) for this lane: issues the load
     auto dir01 = [&](int v) -> uint2 {
-        if (v >= n01) return make_uint2(0u, 0u);
+        if (v >= n_queued) return make_uint2(0u, 0u);
         const uint32_t d = __ldg(variants + v);
         const uint32_t mask = d & kFull;
+        if (Q2 && ((d >> 20) & 3u) == 2u) {                         // class 2 through the queues (short buckets)
+            return live ? __ldg(ix.dir23 + (S9 ^ mask)) : make_uint2(0u, 0u);     // x = first entry, y = count 2 | count 3 << 16
+        }
         uint32_t key = T10 ^ mask;
         bool valid = live;
         if ((d >> 20) & 3u) {
@@ -506,7 +518,7 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
     };
 
     uint2 Bn = PHASE == 0 ? dir01(0) : make_uint2(0u, 0u);
-    for (int v = 0; PHASE == 0 && v < n01; ++v) {
+    for (int v = 0; PHASE == 0 && v < n_queued; ++v) {
         const uint32_t d = __ldg(variants + v);
         const int cls = (int)((d >> 20) & 3u);
         const uint2 B = Bn;
@@ -514,10 +526,11 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
         if (cls != cur_cls) { flush(J0); flush(J1); cur_cls = cls; }   // a queue only ever holds one route family
         if (pend0) eval(J0);
         if (pend1) eval(J1);
-        if (!__any_sync(0xFFFFFFFFu, (B.x | B.y) != 0u)) continue;  // no lane found anything: the common case for small gRNA sets
-        const uint32_t tag = ((uint32_t)lane << 20) | (((d >> 22) & 15u) << 25);
+        if (!__any_sync(0xFFFFFFFFu, (Q2 && cls == 2 ? B.y : (B.x | B.y)) != 0u)) continue;  // no lane found anything: the common case for small gRNA sets
+        const uint32_t tag = ((uint32_t)lane << 27) | (((d >> 22) & 15u) << 20);     // record: [31:27] lane, [23:20] k, entry number below
         uint32_t a0 = B.x >> kSjCountBits01, n0 = B.x & ((1u << kSjCountBits01) - 1u);
         uint32_t a1 = B.y >> kSjCountBits01, n1 = B.y & ((1u << kSjCountBits01) - 1u);
+        if (Q2 && cls == 2) { a0 = B.x; n0 = B.y & 0xFFFFu; a1 = B.x + n0; n1 = B.y >> 16; }
         do {
             // every lane appends up to kSjRound records per table; one scan for both counts (16 bits each)
             const int h0 = (int)min((uint32_t)kSjRound, n0), h1 = (int)min((uint32_t)kSjRound, n1);
@@ -560,10 +573,10 @@ sj_scan_kernel(GenomeView gv, SeedIndexView ix, SjParams prm, const uint32_t* __
     if (PHASE == 1) {
         uint4* items = reinterpret_cast<uint4*>(q0);                // kSjItems x 16 B: x = first entry, y = n2 | nn << 16, z = lane | base << 8
         uint2* ring = reinterpret_cast<uint2*>(items + kSjItems);   // 4 slots x 32 lanes
-        uint2 Cn = dir23(n01);
+        uint2 Cn = dir23(n_queued);
         int t_src = -1;
         SjText Ts = T;
-        for (int v = n01; v < n_variants; ++v) {
+        for (int v = n_queued; v < n_variants; ++v) {
             const uint2 C = Cn;
             Cn = dir23(v + 1);
             uint32_t done = 0u;                                     // entries of this lane's bucket already listed
@@ -634,6 +647,7 @@ __global__ void sj_dirty_blocks_kernel(GenomeView gv, int64_t b0, int64_t b1, un
 
 // [0] candidates (index entries compared with the text), [1] stage-1 survivors of the launches since the last reset, per device
 constexpr int kSjMaxDevices = 64;
+constexpr long long kSjWalkMinN = 400000;            // gRNA: from here the 9-mer buckets are long enough for the cooperative walk
 constexpr int64_t kSjMergeGap = 1024;                // windows
 constexpr size_t kSjMaxRanges = 4096;
 static unsigned long long* g_sj_stats[kSjMaxDevices] = {nullptr};
@@ -669,7 +683,7 @@ bool seedjoin_eligible(const mg_queries* q, const mg_criteria* crit) {
     // Below these sizes the exhaustive kernels are faster: the probes per position (743 with a gap, 436 without) do not depend
     // on the number of gRNA.  One B200, 135 Mb: DP 53 us, pair-word scan 9.6 us, seed-and-join ~1.5 s / N + 4.5 us (gap) or
     // ~0.9 s / N + 1.2 us (no gap) per gRNA.
-    long long min_n = gapless ? 100000 : 30000;
+    long long min_n = gapless ? 100000 : 25000;
     if (const char* m = getenv("MG_SEEDJOIN_MIN")) min_n = atoll(m);
     return q->n >= min_n;
 }
@@ -774,6 +788,11 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     if (e == cudaSuccess && !flat.empty()) e = cudaMemcpyAsync(d_ranges, flat.data(), sizeof(int64_t) * flat.size(), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);              // vars and flat live on this stack frame
     if (e != cudaSuccess) { dev_free(d_vars, s); dev_free(d_ranges, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
+    // The 9-mer buckets hold ~N / 29 000 entries per table: long ones are walked by the whole warp (phase 1), short ones would
+    // leave most lanes idle there and go through the queues of phase 0 like the 10-mer buckets (MG_SJ_WALK_MIN overrides)
+    long long walk_min = kSjWalkMinN;
+    if (const char* w = getenv("MG_SJ_WALK_MIN")) walk_min = atoll(w);
+    const int n_queued = q->n < walk_min ? (int)vars.size() : n01;
     for (int z = 0; z < 2 && e == cudaSuccess; ++z) {
         prm.strand = z == 0 ? 1 : -1;
         // strand windows of the owned forward windows, then the positions that can reach them (w - 1 .. w + 11)
@@ -781,9 +800,12 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         int64_t p0 = std::max<int64_t>(32, ws0 - 2), p1 = std::min<int64_t>(g->glen - 64, ws1 + 12);
         if (p1 <= p0) continue;
         const unsigned grid = (unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps));
-        sj_scan_kernel<0><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
-        if (n01 < (int)vars.size())
-            sj_scan_kernel<1><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+        if (n_queued > n01)
+            sj_scan_kernel<0, true><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+        else
+            sj_scan_kernel<0, false><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+        if (n_queued < (int)vars.size())
+            sj_scan_kernel<1, false><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
