@@ -375,11 +375,20 @@ class MINORg:
                 begin = end
         return out
 
+    def _grna_fasta_dict(self):
+        """The records of self.grna_fasta, read once per (file, modification time, size): filter_background looks at them per
+        subject file, and a 10^6-gRNA FASTA takes seconds to parse."""
+        st = os.stat(self.grna_fasta)
+        key = (self.grna_fasta, st.st_mtime_ns, st.st_size)
+        if getattr(self, "_grna_fasta_cache", (None, None))[0] != key:
+            self._grna_fasta_cache = (key, fasta_to_dict(self.grna_fasta))
+        return self._grna_fasta_cache[1]
+
     def _offtarget_hits(self, fasta_subject, keep_output=False, fout=None, thread=None):
         """ids of the gRNA of self.grna_fasta with a problematic off-target hit in `fasta_subject`."""
         if self.grna_fasta is None:
             self.write_all_grna_fasta()
-        ids_seqs = list(fasta_to_dict(self.grna_fasta).items())
+        ids_seqs = list(self._grna_fasta_dict().items())
         if not ids_seqs:
             return set()
         counts = self.offtarget_counts(fasta_subject, [s for _, s in ids_seqs])
@@ -392,7 +401,7 @@ class MINORg:
             raise MINORgError("MINORg.filter_background requires gRNA (generated with self.grna())")
         if self.grna_fasta is None:
             self.write_all_grna_fasta()
-        self._check_limits({len(s) for s in fasta_to_dict(self.grna_fasta).values()})     # before any device work
+        self._check_limits({len(s) for s in self._grna_fasta_dict().values()})     # before any device work
         ref, query, bg = self._subject_groups()
         files = []
         for enabled, group in (((self.screen_reference or self.query_reference) and ref, ref), (query, query), (bg, bg)):
@@ -425,7 +434,7 @@ class MINORg:
             # one process per GPU: subject files are dealt to the ranks (a single large genome is split by window
             # range instead) and the per-gRNA counts are combined with ONE all-reduce over NCCL
             import torch
-            ids_seqs = list(fasta_to_dict(self.grna_fasta).items())
+            ids_seqs = list(self._grna_fasta_dict().items())
             total = np.zeros(len(ids_seqs), dtype=np.int64)
             if self._window_mode is None and len(files) >= world:
                 for fname in _dist.shard_files(files, rank, world):
@@ -436,7 +445,7 @@ class MINORg:
             t = torch.from_numpy(total).to("cuda")
             _dist.allreduce_counts(t)
             excl = {ids_seqs[i][0] for i in np.nonzero(t.cpu().numpy())[0].tolist()}
-        grna_seqs = fasta_to_dict(self.grna_fasta)
+        grna_seqs = self._grna_fasta_dict()
         failed = {str(grna_seqs[i]).upper() for i in excl}
         passed = {str(s).upper() for s in grna_seqs.values()} - failed
         self.grna_hits.set_seqs_check("background", True, passed)

@@ -302,8 +302,8 @@ class gRNAHits:
                     rows.append([s.id, s.seq, h.target_id, h.target_len, h.parent_sense(mode="str"), h.strand,
                                  a + 1, b, set_no] +
                                 [(s if c in ("GC", "background") else h).check(c, mode="str") for c in checks])
-        for col in (6, 2, 0, 8):
-            rows.sort(key=lambda r, c=col: r[c])
+        # (the reference sorts stably by start, then target id, gRNA id, set: one sort on the reversed key tuple is the same order)
+        rows.sort(key=lambda r: (r[8], r[0], r[2], r[6]))
         with open(fout, "w") as fh:
             for r in [header] + rows:
                 fh.write("\t".join(map(str, r)) + "\n")
