@@ -735,7 +735,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     dev_free(d_n, s); dev_free(d_blocks, s);
     if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
     if (n_dirty > cap) return MG_ERR_UNSUPPORTED;      // a very ragged subject: the DP path takes all of it
-    std::vector<std::pair<int64_t, int64_t>> raw;
+    std::vector<std::pair<int64_t, int64_t>> raw, interior;
     for (const int64_t b : blocks) raw.emplace_back(32 * b - 22, 32 * b + 35);    // windows w with [w-3, w+23) meeting block b
     if (g->n_masks > 0) {                              // windows w with [w-3, w+24) meeting a masked interval (sj_mask_near)
         std::vector<int64_t> ms(g->n_masks), me(g->n_masks);
@@ -745,6 +745,16 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         if (e != cudaSuccess) { set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_CUDA; }
         // the running maximum of the ends gives the same union as the ends themselves (the interval that set it starts earlier)
         for (int i = 0; i < g->n_masks; ++i) raw.emplace_back(ms[i] - 23, me[i] + 3);
+        // Windows whose [w-3, w+24) lies INSIDE one masked interval (span_masked: the last interval starting at or before w-3
+        // has a running-maximum end >= w+24) hold no countable anchor at all - every alignment there (<= 1 gap) is on-target:
+        // neither side screens them.  Only the ~50 windows around each interval edge are left to the exhaustive kernels.
+        for (int i = 0; i < g->n_masks; ++i) {
+            const int64_t a = ms[i] + 3, z = std::min<int64_t>(i + 1 < g->n_masks ? ms[i + 1] + 3 : INT64_MAX, me[i] - 23);
+            if (a < z) {
+                if (!interior.empty() && a <= interior.back().second) interior.back().second = std::max(interior.back().second, z);
+                else interior.emplace_back(a, z);
+            }
+        }
     }
     // Merge (ranges closer than kSjMergeGap windows become one: every range is a separate launch of the exhaustive kernels, the
     // windows in between cost them next to nothing) and clip to the call's windows.  The scan kernel skips exactly these ranges.
@@ -762,8 +772,26 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         }
         dirty_ranges.resize(k);
     }
-    // a subject that is mostly N runs / masked intervals, or cut into very many pieces: the exhaustive kernels take all of it
-    if (dirty_ranges.size() > kSjMaxRanges || 2 * n_delegated_windows > we - wb) { dirty_ranges.clear(); return MG_ERR_UNSUPPORTED; }
+    // the scan kernel skips `skip` = the merged ranges; the caller screens them minus the interiors of the masked intervals
+    const std::vector<std::pair<int64_t, int64_t>> skip = dirty_ranges;
+    if (!interior.empty()) {
+        std::vector<std::pair<int64_t, int64_t>> rest;
+        size_t j = 0;
+        n_delegated_windows = 0;
+        for (const auto& r : skip) {
+            int64_t a = r.first;
+            while (j < interior.size() && interior[j].second <= a) ++j;
+            for (size_t k = j; k < interior.size() && interior[k].first < r.second; ++k) {
+                if (interior[k].first > a) rest.emplace_back(a, interior[k].first);
+                a = std::max(a, interior[k].second);
+            }
+            if (a < r.second) rest.emplace_back(a, r.second);
+        }
+        for (const auto& r : rest) n_delegated_windows += r.second - r.first;
+        dirty_ranges.swap(rest);
+    }
+    // a subject that is mostly N runs / interval edges, or cut into very many pieces: the exhaustive kernels take all of it
+    if (dirty_ranges.size() > kSjMaxRanges || skip.size() > kSjMaxRanges || 2 * n_delegated_windows > we - wb) { dirty_ranges.clear(); return MG_ERR_UNSUPPORTED; }
     // (the >= 64 invalid bases before the first and after the last contig make the windows at both ends of the coordinate
     // space dirty through their blocks, which is what sj_dirty assumes for wf < 3 and wf + 23 > glen)
     SjParams prm;
@@ -780,7 +808,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
     uint32_t* d_vars = nullptr;
     int64_t* d_ranges = nullptr;
     std::vector<int64_t> flat;
-    for (const auto& r : dirty_ranges) { flat.push_back(r.first); flat.push_back(r.second); }
+    for (const auto& r : skip) { flat.push_back(r.first); flat.push_back(r.second); }
     MG_CUDA(dev_alloc((void**)&d_vars, sizeof(uint32_t) * vars.size(), s));
     e = dev_alloc((void**)&d_ranges, sizeof(int64_t) * std::max<size_t>(2, flat.size()), s);
     if (e != cudaSuccess) { dev_free(d_vars, s); set_error("seed join: %s", cudaGetErrorString(e)); return MG_ERR_NOMEM; }
@@ -801,11 +829,11 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         if (p1 <= p0) continue;
         const unsigned grid = (unsigned)((p1 - p0 + 32 * kSjWarps - 1) / (32 * kSjWarps));
         if (n_queued > n01)
-            sj_scan_kernel<0, true><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+            sj_scan_kernel<0, true><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)skip.size(), d_counts, d_stats);
         else
-            sj_scan_kernel<0, false><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+            sj_scan_kernel<0, false><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)skip.size(), d_counts, d_stats);
         if (n_queued < (int)vars.size())
-            sj_scan_kernel<1, false><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)dirty_ranges.size(), d_counts, d_stats);
+            sj_scan_kernel<1, false><<<grid, 32 * kSjWarps, 0, s>>>(gv, iv, prm, d_vars, n01, n_queued, (int)vars.size(), p0, p1, d_ranges, (int)skip.size(), d_counts, d_stats);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
     }
