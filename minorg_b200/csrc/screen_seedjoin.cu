@@ -647,6 +647,7 @@ __global__ void sj_dirty_blocks_kernel(GenomeView gv, int64_t b0, int64_t b1, un
 
 // [0] candidates (index entries compared with the text), [1] stage-1 survivors of the launches since the last reset, per device
 constexpr int kSjMaxDevices = 64;
+constexpr int64_t kSjMinInterior = 8192;             // windows
 constexpr long long kSjWalkMinN = 400000;            // gRNA: from here the 9-mer buckets are long enough for the cooperative walk
 constexpr int64_t kSjMergeGap = 1024;                // windows
 constexpr size_t kSjMaxRanges = 4096;
@@ -750,7 +751,7 @@ int launch_seedjoin(const mg_genome* g, const mg_queries* q, const mg_criteria* 
         // neither side screens them.  Only the ~50 windows around each interval edge are left to the exhaustive kernels.
         for (int i = 0; i < g->n_masks; ++i) {
             const int64_t a = ms[i] + 3, z = std::min<int64_t>(i + 1 < g->n_masks ? ms[i + 1] + 3 : INT64_MAX, me[i] - 23);
-            if (a < z) {
+            if (z - a >= kSjMinInterior) {          // (a short interior costs the exhaustive kernels less than a second range does)
                 if (!interior.empty() && a <= interior.back().second) interior.back().second = std::max(interior.back().second, z);
                 else interior.emplace_back(a, z);
             }

@@ -76,7 +76,9 @@ def test_seedjoin_equals_dp_path_medium(L, M):
     from minorg_b200.ot_regex import make_criteria
     contigs, grnas = _world(100 + M, 3000, [400000, 150000, 37, 0, 90000, 3000])
     names = [c[0] for c in contigs]
-    masks = [(0, 1000, 3000), (0, 2500, 2600), (1, 0, 500), (4, 89000, 90000), (4, 40000, 40010)]
+    # (two long overlapping intervals: their interiors are screened by neither path, only their edges are delegated)
+    masks = [(0, 1000, 3000), (0, 2500, 2600), (1, 0, 500), (4, 89000, 90000), (4, 40000, 40010), (0, 200000, 230000), (0, 225000, 260000),
+             (1, 100000, 120000)]
     genome = L.Genome.from_contigs(contigs)
     genome.set_masks(masks)
     q = L.Queries(grnas)
