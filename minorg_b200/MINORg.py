@@ -19,6 +19,7 @@ from .fasta import fasta_to_dict, read_fasta, reverse_complement
 from . import distributed as _dist
 from .generate_grna import find_multi_gRNA
 from .minimum_set import minimum_sets
+from .minimum_set_nr import minimum_sets_nr
 from .ot_regex import MINORgError, OffTargetExpression, make_criteria
 from .pam import PAM
 
@@ -100,6 +101,7 @@ class MINORg:
         self.final_fasta = None
         self.final_map = None
         self.sets = 1
+        self.prioritise_nr = False                  # parse_config.py:659-662 (--prioritise-nr/--prioritise-pos)
         self.gc_min, self.gc_max = 0.3, 0.7        # parse_config.py:537-540
         self.exclude = None
         self.masked = {}
@@ -488,9 +490,10 @@ class MINORg:
     def minimumset(self, sets=None, manual=None, fasta=None, fout_fasta=None, fout_map=None, fout_eqv=None,
                    report_full_path=True, **_unused_check_switches):
         """Generate `sets` mutually exclusive minimum sets of passing gRNA that each cover all targets and write
-        <prefix>_gRNA_final.fasta / .map (MINORg.py:2530-2650, default non-interactive path: LAR set cover,
-        ties -> closest to 5' -> least redundant -> first).  `manual`, `fasta` renaming and the .eqv file are not
-        provided (outside the hot path)."""
+        <prefix>_gRNA_final.fasta / .map (MINORg.py:2530-2650, non-interactive paths: LAR set cover with ties -> closest
+        to 5' -> least redundant -> first; or, with self.prioritise_nr, the non-redundancy-first covers of
+        minimum_set_nr.py).  `manual`, `fasta` renaming and the .eqv file are not provided (outside the hot path; see
+        DESIGN.md)."""
         if not self.grna_hits:
             raise MINORgError("MINORg.minimumset requires gRNA. You may read a mapping file using"
                               " self.grna_hits.parse_from_mapping('<path to file>') or use self.grna() to generate gRNA.")
@@ -498,7 +501,7 @@ class MINORg:
         targets = {h.target_id for h in self.grna_hits.flatten_hits()}
         self.filter_exclude()
         valid = list(self.valid_grna())
-        grna_sets = minimum_sets(self.grna_hits, valid, sets, targets)
+        grna_sets = (minimum_sets_nr if self.prioritise_nr else minimum_sets)(self.grna_hits, valid, sets, targets)
         fout_fasta = fout_fasta or self.final_fasta or self.results_fname("gRNA_final.fasta")
         fout_map = fout_map or self.final_map or self.results_fname("gRNA_final.map")
         if grna_sets:

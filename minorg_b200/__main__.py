@@ -97,11 +97,16 @@ def main(argv=None):
     _common(s)
     s.add_argument("-m", "--map", required=True)
     s.add_argument("-s", "--set", "--sets", dest="sets", type=int, default=1)
+    s.add_argument("--prioritise-nr", dest="prioritise_nr", action="store_true")
+    s.add_argument("--prioritise-pos", dest="prioritise_nr", action="store_false")
     a = sub.add_parser("full")
     _common(a); _grna_opts(a); _filter_opts(a)
     a.add_argument("-s", "--set", "--sets", dest="sets", type=int, default=1)
+    a.add_argument("--prioritise-nr", dest="prioritise_nr", action="store_true")
+    a.add_argument("--prioritise-pos", dest="prioritise_nr", action="store_false")
     args = ap.parse_args(argv)
     m = _make(args)
+    m.prioritise_nr = bool(getattr(args, "prioritise_nr", False))
     if args.cmd == "grna":
         m.grna()
     elif args.cmd in ("filter", "check"):

@@ -4,7 +4,7 @@ mutually exclusive gRNA sets that each cover every target, by the LAR set-cover 
 are already covered, then by first occurrence (minimum_set.py:719-782, MINORg.py:2606-2608).
 
 Host-side combinatorics on <= 10^3 items - no kernel here.  The non-redundancy-first
-variant (prioritise_nr, minweight_sc.py) is not provided.  Pinned by tests/golden/minimumset.json, produced by
+variant (prioritise_nr, minweight_sc.py) is minimum_set_nr.py.  Pinned by tests/golden/minimumset.json, produced by
 executing the reference's make_get_minimum_set."""
 
 

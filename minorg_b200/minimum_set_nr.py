@@ -1,0 +1,217 @@
+"""Minimum-set step with non-redundancy as the priority - `MINORg.minimumset` with `prioritise_nr=True`
+(MINORg.py:2606-2615 -> minimum_set.py:639-716 `make_set_cover_nr` -> :470-553 `limited_minweight_SC`, :385-444
+`limited_optimal_SC` -> minweight_sc.py:241-354, the enumeration of Ajami & Cohen 2019 as the reference adapted it).
+
+gRNA with identical target coverage are collapsed into coverage groups (`gRNAHits.collapse`); set covers are sought over the
+GROUPS: a bounded enumeration of approximately minimum-weight covers seeded with every group in turn (weight = coverage
+size), plus every exact cover of at most five groups inside the redundancy the enumeration reached.  Covers are ranked by
+(number of groups, redundancy, - largest coverage); a gRNA set takes the gRNA closest to the 5' end from every group of the
+best cover, and the next set takes the next ones, until a group runs dry and the next cover takes over.
+
+Host-side combinatorics on tens of groups - no kernel here.  Where the reference walks a Python `set`
+of objects hashed by name (so that ties are broken differently from run to run, minweight_sc.py:127-160), this file walks the
+groups in their collapse order, and gRNA at the same distance from the 5' end in gRNA order.  Pinned by
+tests/golden/minimumset_nr.json: the reference's own `make_get_minimum_set` on 32 inputs, executed under eight hash seeds - the
+29 rows on which the reference agrees with itself are matched exactly; on the other three (two gRNA of a group tie on position)
+the sets have the reference's sizes, cover every target and are mutually exclusive."""
+
+INF = float("inf")
+
+
+class _Groups:
+    """The coverage groups of a gRNA set: index = collapse order; cov[i] = frozenset of target ids; members[i] = gRNA
+    sequences still available, closest to the 5' end first."""
+
+    def __init__(self, grna_hits, seqs):
+        self.cov, self.members = [], []
+        for _name, cov, members in grna_hits.collapse(seqs=seqs):
+            ordered = sorted((gs.seq for gs in members), key=grna_hits.relative_5prime_pos)     # stable: ties keep gRNA order
+            self.cov.append(frozenset(cov))
+            self.members.append(ordered)
+
+    def weight(self, C):
+        return sum(len(self.cov[i]) for i in C) if C else INF
+
+    def elements(self, C):
+        out = set()
+        for i in C:
+            out |= self.cov[i]
+        return out
+
+    def redundancy(self, C):
+        return sum(len(self.cov[i]) for i in C) - len(self.elements(C))
+
+
+def _greedy_cover(G, U, S, seed=None, penalty=0.0):
+    """approx_min_SC (minweight_sc.py:241-274): repeatedly the group with the smallest weight per newly covered target
+    (+ penalty per target it leaves uncovered), larger groups first among equals.  False if S cannot cover U."""
+    U = set(U)
+    if U - G.elements(S):
+        return False
+    C = []
+    if seed is not None:
+        S = [i for i in S if i != seed]
+        C.append(seed)
+        U -= G.cov[seed]
+    while U:
+        best, best_key = None, None
+        for i in S:
+            cover = len(U & G.cov[i])
+            if cover:
+                wc = len(G.cov[i]) / cover
+                key = (wc + len(U - G.cov[i]) * wc * penalty, -len(G.cov[i]))
+            else:
+                key = (INF, -len(G.cov[i]))
+            if best_key is None or key < best_key:
+                best, best_key = i, key
+        C.append(best)
+        U -= G.cov[best]
+    return frozenset(C)
+
+
+def _lightest(G, S):
+    return min(S, key=lambda i: len(G.cov[i]))
+
+
+def _enumerate_covers(G, U, S, n_iter, seed, penalty):
+    """enum_approx_order_SC (minweight_sc.py:286-350) with the reference's queue discipline: the entry with the lightest
+    cover is expanded, the FIRST entry of the queue is dropped."""
+    out, q1, q2 = [], [], []
+    S = sorted(S)
+    C = _greedy_cover(G, U, S, seed=seed, penalty=penalty)
+    if C:
+        q1.append((C, frozenset(), frozenset(S)))
+    for _ in range(n_iter):
+        if not q1 and not q2:
+            break
+        w1 = G.weight(q1[0][0]) if q1 else INF
+        w2 = G.weight(q2[0][0]) if q2 else INF
+        if w1 <= w2:
+            C, fixed, pool = min(q1, key=lambda e: G.weight(e[0]))
+            out.append(C)
+            rest = pool - C
+            if rest:
+                s = _lightest(G, sorted(rest))
+                q2.append((C | {s}, frozenset([s]), rest - {s}))
+            for s in sorted(C - fixed):
+                pool = pool - {s}
+                sub = _greedy_cover(G, U - G.elements(fixed), sorted(pool), penalty=penalty)
+                if sub is not False:
+                    q1.append((sub | fixed, fixed, pool))
+                fixed = fixed | {s}
+            q1.pop(0)
+        else:
+            C, chosen, pool = min(q2, key=lambda e: G.weight(e[0]))
+            out.append(C)
+            if pool:
+                s = _lightest(G, sorted(pool))
+                q2.append(((C | {s}) - chosen, frozenset([s]), pool - {s}))
+                q2.append((C | {s}, frozenset([s]), pool - {s}))
+            q2.pop(0)
+    return out
+
+
+def _minweight_covers(G, live, targets, n_sets, penalty):
+    """limited_minweight_SC (minimum_set.py:470-553): seed the enumeration with every group, widest coverage first, drop the
+    groups of a coverage size once they have all been seeds, stop when a seed covers too little to matter."""
+    n_iter, n_track = max(20, 2 * n_sets), max(10, 2 * n_sets)
+    n_targets = len(targets)
+    solutions, shortest = [], [n_targets]
+    by_size = {}
+    for i in live:
+        by_size.setdefault(len(G.cov[i]), []).append(i)
+    live = list(live)
+
+    def track(covers):
+        return sorted(shortest + [len(C) for C in covers if len(C) <= shortest[-1]])[:n_track]
+
+    if n_targets in by_size:
+        full = by_size.pop(n_targets)
+        live = [i for i in live if i not in full]
+        new = [frozenset([i]) for i in full]
+        solutions.extend(new)
+        shortest = track(new)
+    for size in sorted(by_size, reverse=True):
+        if size < (1 if len(shortest) < n_track else n_targets / shortest[-1]):
+            break
+        found = []
+        for seed in by_size[size]:
+            found.extend(_enumerate_covers(G, targets, live, n_iter, seed, penalty))
+        shortest = track(found)
+        keep = [C for C in solutions if len(C) <= shortest[-1]]
+        for C in found:
+            if len(C) <= shortest[-1] and C not in keep:
+                keep.append(C)
+        solutions = keep
+        live = [i for i in live if i not in by_size[size]]
+    return solutions
+
+
+def _exact_covers(G, groups, targets, size, max_redundancy):
+    """limited_optimal_SC (minimum_set.py:385-444): every cover of at most `size` groups with redundancy <= max_redundancy,
+    groups tried from the widest."""
+    order = sorted(groups, key=lambda i: -len(G.cov[i]))
+    suffix = [set() for _ in range(len(order) + 1)]
+    for k in range(len(order) - 1, -1, -1):
+        suffix[k] = suffix[k + 1] | G.cov[order[k]]
+    out = []
+
+    def grow(C, have, start, depth):
+        if depth >= size or (targets - have - suffix[start]):
+            return
+        need = int(len(targets - have) / (size - depth) + 1)
+        for k in range(start, len(order)):
+            i = order[k]
+            if len(G.cov[i]) < need:
+                break
+            if not G.cov[i] < have:
+                Cb = C + [i]
+                if G.redundancy(Cb) > max_redundancy:
+                    continue
+                if have | G.cov[i] == targets:
+                    out.append(frozenset(Cb))
+                else:
+                    grow(Cb, have | G.cov[i], k + 1, depth + 1)
+
+    grow([], set(), 0, 0)
+    return out
+
+
+def minimum_sets_nr(grna_hits, seqs, n_sets, targets=None, low_coverage_penalty=0.5, optimal_depth=5):
+    """Up to n_sets mutually exclusive gRNA sets (lists of sequences) that each cover every target, non-redundancy first.
+    The reference builds its cover list for ONE set (make_get_minimum_set's num_sets default) whatever the number of sets
+    asked for; so does this."""
+    G = _Groups(grna_hits, seqs)
+    all_groups = list(range(len(G.cov)))
+    targets = set(targets) if targets else G.elements(all_groups)
+    live = list(all_groups)
+
+    def covers():
+        usable = [i for i in live]
+        mw = _minweight_covers(G, usable, targets, 1, low_coverage_penalty)
+        if not mw:
+            return []
+        depth = min(optimal_depth, max(len(C) for C in mw))
+        red = max(G.redundancy(C) for C in mw) / len(targets)
+        exact = [C for C in _exact_covers(G, all_groups, targets, depth, red * len(targets)) if C not in mw]
+        ranked = mw + exact
+        ranked.sort(key=lambda C: (len(C), G.redundancy(C), -max(len(G.cov[i]) for i in C)))
+        return ranked
+
+    ranked = covers()
+    out = []
+    while len(out) < n_sets:
+        if not ranked:
+            break
+        while ranked and not all(G.members[i] for i in ranked[0]):
+            ranked.pop(0)
+            if not ranked:
+                live = [i for i in live if G.members[i]]
+                ranked = covers()
+                if not ranked:
+                    break
+        if not ranked:
+            break
+        cover = sorted(ranked[0], key=lambda i: (-len(G.cov[i]), sorted(G.cov[i])))
+        out.append([G.members[i].pop(0) for i in cover])
+    return out

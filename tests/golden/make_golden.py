@@ -592,3 +592,67 @@ def gen_mapfile():
 
 if __name__ == "__main__" and "mapfile" in sys.argv[1:]:
     gen_mapfile()
+
+
+# ----------------------------------------------------------------------------- minimum set, prioritise_nr
+def _nr_rows():
+    """The reference's non-redundancy-first minimum-set path exactly as MINORg.minimumset runs it with prioritise_nr=True
+    (MINORg.py:2606-2615 -> minimum_set.make_get_minimum_set -> make_set_cover_nr -> minweight_sc)."""
+    import copy
+    import hashlib
+    from minorg.minimum_set import make_get_minimum_set
+    rows = []
+    srcs = [("synth_targets.fasta", ".NGG", 20), ("sample_CDS.fasta", ".NGG", 20), ("sample_CDS.fasta", "TTTV.", 23),
+            ("config1/targets.fasta", ".NGG", 20), ("sample_CDS.fasta", "ATV.", 20),
+            ("synth_cover.fasta", ".NGG", 20), ("synth_cover.fasta", "TTN", 18), ("synth_cover.fasta", ".NG", 20)]
+    for label, pam, L in srcs:
+        for n_sets in (1, 3):
+            for drop in (5, 2):
+                h = quiet(ref_find_multi_gRNA, os.path.join(HERE, label), pam=pam, gRNA_len=L)
+                h.assign_seqid()
+                failed = [s for s in h.seqs if int(hashlib.md5(s.encode()).hexdigest(), 16) % drop == 0]
+                h.set_seqs_check("background", True, [s for s in h.seqs if s not in failed])
+                h.set_seqs_check("background", False, failed)
+                valid = copy.deepcopy(quiet(h.filter_seqs, "background", accept_invalid=False, accept_invalid_field=True,
+                                            quiet=True, report_invalid_field=True))
+                targets = set(hit.target_id for hit in h.flatten_hits())
+                sets, err = [], None
+                try:
+                    get = quiet(make_get_minimum_set, copy.deepcopy(valid), prioritise_nr=True, manual_check=False, targets=targets,
+                                suppress_warning=True)
+                    while len(sets) < n_sets:
+                        s = quiet(get)
+                        if not s:
+                            break
+                        sets.append(sorted(s))
+                except Exception as e:
+                    err = type(e).__name__
+                rows.append(dict(fasta=label, pam=pam, L=L, n_sets=n_sets, drop=drop, failed=failed, sets=sets, error=err))
+    return rows
+
+
+def gen_minimumset_nr():
+    """Rows that come out identical under eight hash seeds (the reference iterates Python sets of objects hashed by name in
+    several places, minweight_sc.py:127-160): run this file eight times as a subprocess and mark what agrees."""
+    import subprocess
+    runs = []
+    for seed in ("0", "1", "2", "3", "4", "5", "6", "7"):
+        env = dict(os.environ, PYTHONHASHSEED=seed)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "_nr_rows"], env=env, capture_output=True, text=True)
+        runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    rows = []
+    for versions in zip(*runs):
+        a = versions[0]
+        a["stable_across_hash_seeds"] = all(v["sets"] == a["sets"] and v["error"] == a["error"] for v in versions)
+        rows.append(a)
+        print("  minimumset_nr", a["fasta"], a["pam"], a["n_sets"], a["drop"], "->", [len(s) for s in a["sets"]], a["error"],
+              "stable" if a["stable_across_hash_seeds"] else "UNSTABLE")
+    dump("minimumset_nr.json", dict(rows=rows))
+
+
+if __name__ == "__main__" and "_nr_rows" in sys.argv[1:]:
+    print(json.dumps(_nr_rows()))
+    sys.exit(0)
+
+if __name__ == "__main__" and "minimumset_nr" in sys.argv[1:]:
+    gen_minimumset_nr()

@@ -235,3 +235,41 @@ def test_large_grna_set_takes_the_seed_and_join_screen_with_the_same_verdicts(tm
     assert ran[0]
     assert verdicts[0] == verdicts[1]
     assert 100 < sum(v is False for v in verdicts[0]) < len(verdicts[0])
+
+
+def test_minimumset_prioritise_nr_through_the_class_and_cli(cfg1, tmp_path):
+    """self.prioritise_nr / --prioritise-nr: mutually exclusive sets that each cover every target, equal to what
+    minimum_set_nr.minimum_sets_nr picks from the passing gRNA (itself pinned to the reference on the CPU)."""
+    from minorg_b200.MINORg import MINORg
+    from minorg_b200.__main__ import main
+    from minorg_b200.minimum_set_nr import minimum_sets_nr
+    m = MINORg(directory=str(tmp_path / "nr"), prefix="nr")
+    m.target = str(cfg1 / "targets.fasta")
+    m.add_query(str(cfg1 / "subset_9654.fasta"), alias="9654")
+    m.ot_mismatch = 2
+    m.prioritise_nr = True
+    m.grna()
+    m.filter_background()
+    sets = m.minimumset(sets=3)
+    targets = {h.target_id for h in m.grna_hits.flatten_hits()}
+    assert len(sets) == 3
+    used = [s for g in sets for s in g]
+    assert len(used) == len(set(used))
+    for g in sets:
+        assert {h.target_id for s in g for h in m.grna_hits.get_hits(s)} >= targets
+    assert sets == minimum_sets_nr(m.grna_hits, list(m.valid_grna()), 3, targets)
+    rows = [l.split("\t") for l in open(m.final_map).read().splitlines()[1:]]
+    assert {r[1] for r in rows} == set(used) and {r[8] for r in rows} == {"1", "2", "3"}
+    m.close()
+    out = tmp_path / "cli_nr"
+    assert main(["full", "-d", str(out), "--prefix", "run", "-t", str(cfg1 / "targets.fasta"), "-q", str(cfg1 / "subset_9654.fasta"),
+                 "--ot-mismatch", "2", "-s", "3", "--prioritise-nr"]) == 0
+    rows2 = [l.split("\t") for l in open(out / "run" / "run_gRNA_final.map").read().splitlines()[1:]]
+    # (the CLI also applies the GC filter, so its candidate pool differs: three exclusive covers of every target all the same)
+    by_set = {}
+    for r in rows2:
+        by_set.setdefault(r[8], []).append(r)
+    assert set(by_set) == {"1", "2", "3"}
+    assert all({r[2] for r in rs} >= targets for rs in by_set.values())
+    seqs_of = [{r[1] for r in rs} for rs in by_set.values()]
+    assert not (seqs_of[0] & seqs_of[1]) and not (seqs_of[0] & seqs_of[2]) and not (seqs_of[1] & seqs_of[2])

@@ -455,3 +455,34 @@ def test_map_reader_matches_reference_on_its_fixture(golden, tmp_path):
         n += 1
     assert n == 4
 
+
+
+def test_minimum_sets_nr_match_reference(golden):
+    """prioritise_nr path (minimum_set_nr.py) vs the reference's make_get_minimum_set(prioritise_nr=True), executed under eight
+    hash seeds: exact on the rows where the reference agrees with itself; on the rows where it does not (two gRNA of a
+    coverage group tie on position and the reference takes whichever its hash-ordered set yields first) the sets have the
+    reference's sizes, cover every target and are mutually exclusive."""
+    import os
+    from minorg_b200.minimum_set_nr import minimum_sets_nr
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    rows = golden("minimumset_nr.json")["rows"]
+    stable = [r for r in rows if r["stable_across_hash_seeds"]]
+    assert len(rows) >= 32 and len(stable) >= 29 and any(len(r["sets"][0]) >= 4 for r in stable)
+    for r in rows:
+        assert r["error"] is None
+        h = _hits_from_oracle(O.find_multi_grna(os.path.join(gdir, r["fasta"]), r["pam"], r["L"]))
+        h.assign_seqid()
+        h.set_seqs_check("background", True, [s for s in h.seqs if s not in r["failed"]])
+        h.set_seqs_check("background", False, r["failed"])
+        valid = h.filter_seqs("background")
+        got = minimum_sets_nr(h, valid, r["n_sets"])
+        key = (r["fasta"], r["pam"], r["n_sets"], r["drop"])
+        if r["stable_across_hash_seeds"]:
+            assert [sorted(s) for s in got] == r["sets"], key
+        else:
+            assert [len(s) for s in got] == [len(s) for s in r["sets"]], key
+        targets = {hit.target_id for hit in h.flatten_hits()}
+        used = [s for group in got for s in group]
+        assert len(used) == len(set(used)) and set(used) <= set(valid), key
+        for group in got:
+            assert {hit.target_id for s in group for hit in h.get_hits(s)} >= targets, key
