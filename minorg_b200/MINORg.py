@@ -47,6 +47,16 @@ class Masked:
         return a >= self.start and b <= self.end
 
 
+def _manual_check_prompt(set_num, listed):
+    """The reference's terminal dialogue for one drawn gRNA set (minimum_set.py:43-64)."""
+    print("\n\tID\tsequence (Set %d)" % set_num)
+    for gid, seq in listed:
+        print("\t%s\t%s" % (gid, seq))
+    return input("Hit 'x' to continue if you are satisfied with these sequences."
+                 " Otherwise, enter the sequence ID (case-sensitive) or sequence of"
+                 " an undesirable gRNA and hit the return key to update this list: ")
+
+
 def _fname(x):
     return getattr(x, "filename", None) or getattr(x, "fasta", None) or str(x)
 
@@ -492,8 +502,9 @@ class MINORg:
         """Generate `sets` mutually exclusive minimum sets of passing gRNA that each cover all targets and write
         <prefix>_gRNA_final.fasta / .map (MINORg.py:2530-2650, non-interactive paths: LAR set cover with ties -> closest
         to 5' -> least redundant -> first; or, with self.prioritise_nr, the non-redundancy-first covers of
-        minimum_set_nr.py).  `manual`, `fasta` renaming and the .eqv file are not provided (outside the hot path; see
-        DESIGN.md)."""
+        minimum_set_nr.py).  manual=True shows every drawn set on the terminal and lets the user reject gRNA by id or
+        sequence before it is accepted (minimum_set.py:43-64, 603-637; the reference's default unless --auto, here opt-in).
+        `fasta` renaming and the .eqv file are not provided (outside the hot path)."""
         if not self.grna_hits:
             raise MINORgError("MINORg.minimumset requires gRNA. You may read a mapping file using"
                               " self.grna_hits.parse_from_mapping('<path to file>') or use self.grna() to generate gRNA.")
@@ -501,7 +512,8 @@ class MINORg:
         targets = {h.target_id for h in self.grna_hits.flatten_hits()}
         self.filter_exclude()
         valid = list(self.valid_grna())
-        grna_sets = (minimum_sets_nr if self.prioritise_nr else minimum_sets)(self.grna_hits, valid, sets, targets)
+        grna_sets = (minimum_sets_nr if self.prioritise_nr else minimum_sets)(self.grna_hits, valid, sets, targets,
+                                                                             review=_manual_check_prompt if manual else None)
         fout_fasta = fout_fasta or self.final_fasta or self.results_fname("gRNA_final.fasta")
         fout_map = fout_map or self.final_map or self.results_fname("gRNA_final.map")
         if grna_sets:

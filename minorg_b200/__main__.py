@@ -99,11 +99,15 @@ def main(argv=None):
     s.add_argument("-s", "--set", "--sets", dest="sets", type=int, default=1)
     s.add_argument("--prioritise-nr", dest="prioritise_nr", action="store_true")
     s.add_argument("--prioritise-pos", dest="prioritise_nr", action="store_false")
+    s.add_argument("--manual", dest="manual", action="store_true", help="approve every gRNA set at the terminal")
+    s.add_argument("--auto", dest="manual", action="store_false")
     a = sub.add_parser("full")
     _common(a); _grna_opts(a); _filter_opts(a)
     a.add_argument("-s", "--set", "--sets", dest="sets", type=int, default=1)
     a.add_argument("--prioritise-nr", dest="prioritise_nr", action="store_true")
     a.add_argument("--prioritise-pos", dest="prioritise_nr", action="store_false")
+    a.add_argument("--manual", dest="manual", action="store_true", help="approve every gRNA set at the terminal")
+    a.add_argument("--auto", dest="manual", action="store_false")
     args = ap.parse_args(argv)
     m = _make(args)
     m.prioritise_nr = bool(getattr(args, "prioritise_nr", False))
@@ -115,11 +119,11 @@ def main(argv=None):
         _do_filter(m, args)
     elif args.cmd == "minimumset":
         _load_map(m, args.map)
-        m.minimumset(sets=args.sets)
+        m.minimumset(sets=args.sets, manual=bool(getattr(args, "manual", False)))
     else:
         m.grna()
         _do_filter(m, args)
-        m.minimumset(sets=args.sets)
+        m.minimumset(sets=args.sets, manual=bool(getattr(args, "manual", False)))
     m.close()
     return 0
 

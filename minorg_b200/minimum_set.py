@@ -52,20 +52,55 @@ def set_cover_lar(coverage):
     return list(chosen)
 
 
-def minimum_sets(grna_hits, seqs, n_sets, targets=None):
+def review_answer(grna_hits, picked, answer):
+    """What the manual check does with an answer (minimum_set.py:618-636): 'x' accepts (None); the id or the sequence of a
+    listed gRNA rejects it (its index in `picked`); anything else is invalid (-1).  (The reference looks an id up exactly and
+    a sequence in upper case - and raises ValueError on a sequence typed in lower case; here case does not matter.)"""
+    if answer.upper() == "X":
+        return None
+    ids = [grna_hits.get_gRNAseq_by_seq(s).id for s in picked]
+    if answer in ids:
+        return ids.index(answer)
+    upper = [str(s).upper() for s in picked]
+    if answer.upper() in upper:
+        return upper.index(answer.upper())
+    print("Invalid input.")
+    return -1
+
+
+def listed_for_review(grna_hits, picked):
+    """(id, sequence) of a drawn set in the order the reference prints it: by gRNA id (minimum_set.py:616)."""
+    return sorted(((grna_hits.get_gRNAseq_by_seq(s).id, s) for s in picked), key=lambda x: x[0])
+
+
+def minimum_sets(grna_hits, seqs, n_sets, targets=None, review=None):
     """Up to n_sets mutually exclusive covers drawn from `seqs` (candidate order = order of `seqs`).
-    Stops early when the remaining candidates can no longer cover every target (minimum_set.py:848-855)."""
+    Stops early when the remaining candidates can no longer cover every target (minimum_set.py:848-855).
+    review (manual mode, minimum_set.py:603-637): called with (set number, [(id, sequence)]) for every drawn set; it returns
+    'x' to accept, or the id / sequence of a gRNA to reject - the set is then drawn again without it (the other gRNA of the
+    rejected draw go back to the END of the candidate order, as in the reference, :850-851)."""
     coverage = {s: list(grna_hits.get_hits(s)) for s in seqs}
     targets = set(targets) if targets else {h.target_id for hits in coverage.values() for h in hits}
+    taken = {}
     out = []
     while len(out) < n_sets:
-        reachable = {h.target_id for hits in coverage.values() for h in hits}
-        if not coverage or not reachable >= targets:
-            break
-        picked = set_cover_lar(coverage)
+        give_back = []
+        while True:
+            for s in give_back:
+                coverage[s] = taken.pop(s)
+            reachable = {h.target_id for hits in coverage.values() for h in hits}
+            picked = set_cover_lar(coverage) if coverage and reachable >= targets else []
+            for s in picked:
+                taken[s] = coverage.pop(s)
+            if not picked or review is None:
+                break
+            verdict = review_answer(grna_hits, picked, review(len(out) + 1, listed_for_review(grna_hits, picked)))
+            if verdict is None:
+                break
+            if verdict >= 0:
+                del picked[verdict]
+            give_back = picked
         if not picked:
             break
-        for s in picked:
-            del coverage[s]
         out.append(picked)
     return out

@@ -177,10 +177,12 @@ def _exact_covers(G, groups, targets, size, max_redundancy):
     return out
 
 
-def minimum_sets_nr(grna_hits, seqs, n_sets, targets=None, low_coverage_penalty=0.5, optimal_depth=5):
+def minimum_sets_nr(grna_hits, seqs, n_sets, targets=None, low_coverage_penalty=0.5, optimal_depth=5, review=None):
     """Up to n_sets mutually exclusive gRNA sets (lists of sequences) that each cover every target, non-redundancy first.
     The reference builds its cover list for ONE set (make_get_minimum_set's num_sets default) whatever the number of sets
-    asked for; so does this."""
+    asked for; so does this.  review: the manual check, see minimum_set.minimum_sets (the gRNA of a rejected draw go back to
+    their coverage groups, minimum_set.py:691-696)."""
+    from .minimum_set import listed_for_review, review_answer
     G = _Groups(grna_hits, seqs)
     all_groups = list(range(len(G.cov)))
     targets = set(targets) if targets else G.elements(all_groups)
@@ -199,19 +201,37 @@ def minimum_sets_nr(grna_hits, seqs, n_sets, targets=None, low_coverage_penalty=
         return ranked
 
     ranked = covers()
-    out = []
-    while len(out) < n_sets:
-        if not ranked:
-            break
+
+    def draw():
+        """[(group, sequence)] from the best cover whose groups all still hold a gRNA; [] when no cover is left."""
+        nonlocal ranked, live
         while ranked and not all(G.members[i] for i in ranked[0]):
             ranked.pop(0)
             if not ranked:
                 live = [i for i in live if G.members[i]]
                 ranked = covers()
-                if not ranked:
-                    break
         if not ranked:
-            break
+            return []
         cover = sorted(ranked[0], key=lambda i: (-len(G.cov[i]), sorted(G.cov[i])))
-        out.append([G.members[i].pop(0) for i in cover])
+        return [(i, G.members[i].pop(0)) for i in cover]
+
+    out = []
+    while len(out) < n_sets and ranked:
+        give_back = []
+        while True:
+            for i, s in give_back:
+                G.members[i].insert(0, s)
+            picked = draw()
+            if not picked or review is None:
+                break
+            seqs_only = [s for _, s in picked]
+            verdict = review_answer(grna_hits, seqs_only, review(len(out) + 1, listed_for_review(grna_hits, seqs_only)))
+            if verdict is None:
+                break
+            if verdict >= 0:
+                del picked[verdict]
+            give_back = picked
+        if not picked:
+            break
+        out.append([s for _, s in picked])
     return out

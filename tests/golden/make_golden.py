@@ -656,3 +656,80 @@ if __name__ == "__main__" and "_nr_rows" in sys.argv[1:]:
 
 if __name__ == "__main__" and "minimumset_nr" in sys.argv[1:]:
     gen_minimumset_nr()
+
+
+# ----------------------------------------------------------------------------- minimum set, manual (interactive) mode
+def _manual_rows():
+    """make_get_minimum_set(manual_check=True) with scripted answers in place of the terminal (minimum_set.py:43-64, 603-637):
+    every set is shown; the script rejects the first listed gRNA by SEQUENCE, then the first listed gRNA of the re-drawn set by
+    ID, types something invalid, then accepts with 'x'; the second set is accepted at once."""
+    import builtins
+    import copy
+    import hashlib
+    import minorg.minimum_set as ms
+    from minorg.minimum_set import make_get_minimum_set, all_best_nr, all_best_pos
+    rows = []
+    srcs = [("synth_targets.fasta", ".NGG", 20), ("config1/targets.fasta", ".NGG", 20), ("synth_cover.fasta", ".NGG", 20),
+            ("synth_cover.fasta", "TTN", 18)]
+    for label, pam, L in srcs:
+        for nr in (False, True):
+            h = quiet(ref_find_multi_gRNA, os.path.join(HERE, label), pam=pam, gRNA_len=L)
+            h.assign_seqid()
+            failed = [s for s in h.seqs if int(hashlib.md5(s.encode()).hexdigest(), 16) % 5 == 0]
+            h.set_seqs_check("background", True, [s for s in h.seqs if s not in failed])
+            h.set_seqs_check("background", False, failed)
+            valid = copy.deepcopy(quiet(h.filter_seqs, "background", accept_invalid=False, accept_invalid_field=True,
+                                        quiet=True, report_invalid_field=True))
+            targets = set(hit.target_id for hit in h.flatten_hits())
+            shown, state = [], {"n": 0}
+
+            def prompt(grnas, set_num=None, _shown=shown, _state=state):
+                listed = [(g.id, str(g.seq)) for g in grnas]
+                _shown.append([set_num, listed])
+                _state["n"] += 1
+                k = _state["n"]
+                return {1: listed[0][1], 2: listed[0][0], 3: "no such gRNA"}.get(k, "x")
+            real = ms.manual_check_prompt
+            ms.manual_check_prompt = prompt
+            tie = (lambda *a: tuple()) if nr else \
+                (lambda cov, all_cov, covered: tuple(all_best_nr(all_best_pos(cov, all_cov, covered), all_cov, covered).items())[0])
+            sets, err = [], None
+            try:
+                get = quiet(make_get_minimum_set, copy.deepcopy(valid), prioritise_nr=nr, manual_check=True, targets=targets,
+                            tie_breaker=tie, suppress_warning=True)
+                while len(sets) < 2:
+                    s = quiet(get)
+                    if not s:
+                        break
+                    sets.append(sorted(s))
+            except Exception as e:
+                err = type(e).__name__
+            finally:
+                ms.manual_check_prompt = real
+            rows.append(dict(fasta=label, pam=pam, L=L, prioritise_nr=nr, failed=failed, sets=sets, shown=shown, error=err))
+    return rows
+
+
+def gen_minimumset_manual():
+    import subprocess
+    runs = []
+    for seed in ("0", "1", "2", "3", "4", "5"):
+        env = dict(os.environ, PYTHONHASHSEED=seed)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "_manual_rows"], env=env, capture_output=True, text=True)
+        runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    rows = []
+    for versions in zip(*runs):
+        a = versions[0]
+        a["stable_across_hash_seeds"] = all(v["sets"] == a["sets"] and v["shown"] == a["shown"] and v["error"] == a["error"] for v in versions)
+        rows.append(a)
+        print("  minimumset_manual", a["fasta"], a["pam"], "nr" if a["prioritise_nr"] else "pos", "->", [len(s) for s in a["sets"]],
+              len(a["shown"]), "prompts", a["error"], "stable" if a["stable_across_hash_seeds"] else "UNSTABLE")
+    dump("minimumset_manual.json", dict(rows=rows))
+
+
+if __name__ == "__main__" and "_manual_rows" in sys.argv[1:]:
+    print(json.dumps(_manual_rows()))
+    sys.exit(0)
+
+if __name__ == "__main__" and "minimumset_manual" in sys.argv[1:]:
+    gen_minimumset_manual()

@@ -260,6 +260,27 @@ def test_minimumset_prioritise_nr_through_the_class_and_cli(cfg1, tmp_path):
     assert sets == minimum_sets_nr(m.grna_hits, list(m.valid_grna()), 3, targets)
     rows = [l.split("\t") for l in open(m.final_map).read().splitlines()[1:]]
     assert {r[1] for r in rows} == set(used) and {r[8] for r in rows} == {"1", "2", "3"}
+    # manual mode through the class: scripted terminal answers (reject the first listed gRNA of set 1, then accept everything)
+    import builtins
+    answers = iter([open(m.final_map).read().splitlines()[1].split("\t")[1], "x", "x", "x", "x"])
+    real_input = builtins.input
+    builtins.input = lambda *_a: next(answers)
+    try:
+        m2 = MINORg(directory=str(tmp_path / "manual"), prefix="man")
+        m2.target = str(cfg1 / "targets.fasta")
+        m2.add_query(str(cfg1 / "subset_9654.fasta"), alias="9654")
+        m2.ot_mismatch = 2
+        m2.grna()
+        m2.filter_background()
+        auto = m2.minimumset(sets=1)
+        rejected = sorted((m2.grna_hits.get_gRNAseq_by_seq(s).id, s) for s in auto[0])[0][1]
+        answers = iter([rejected, "x"])
+        manual = m2.minimumset(sets=1, manual=True)
+        assert rejected in auto[0] and rejected not in manual[0]
+        assert {h.target_id for s in manual[0] for h in m2.grna_hits.get_hits(s)} >= targets
+        m2.close()
+    finally:
+        builtins.input = real_input
     m.close()
     out = tmp_path / "cli_nr"
     assert main(["full", "-d", str(out), "--prefix", "run", "-t", str(cfg1 / "targets.fasta"), "-q", str(cfg1 / "subset_9654.fasta"),

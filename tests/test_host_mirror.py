@@ -486,3 +486,38 @@ def test_minimum_sets_nr_match_reference(golden):
         assert len(used) == len(set(used)) and set(used) <= set(valid), key
         for group in got:
             assert {hit.target_id for s in group for hit in h.get_hits(s)} >= targets, key
+
+
+def test_minimum_sets_manual_mode_matches_reference(golden):
+    """Manual (interactive) mode of both minimum-set paths vs the reference's make_get_minimum_set(manual_check=True) driven by
+    scripted answers (reject the first listed gRNA by sequence, the first of the re-drawn set by id, an invalid entry, 'x';
+    the second set accepted at once): the sets SHOWN at every prompt and the final sets are the reference's."""
+    import os
+    from minorg_b200.minimum_set import minimum_sets
+    from minorg_b200.minimum_set_nr import minimum_sets_nr
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    rows = golden("minimumset_manual.json")["rows"]
+    assert len(rows) >= 8 and sum(r["stable_across_hash_seeds"] for r in rows) >= 7
+    for r in rows:
+        assert r["error"] is None and len(r["shown"]) == 5
+        h = _hits_from_oracle(O.find_multi_grna(os.path.join(gdir, r["fasta"]), r["pam"], r["L"]))
+        h.assign_seqid()
+        h.set_seqs_check("background", True, [s for s in h.seqs if s not in r["failed"]])
+        h.set_seqs_check("background", False, r["failed"])
+        valid = h.filter_seqs("background")
+        shown = []
+
+        def review(set_no, listed, _shown=shown):
+            _shown.append([set_no, [list(x) for x in listed]])
+            k = len(_shown)
+            return {1: listed[0][1], 2: listed[0][0], 3: "no such gRNA"}.get(k, "x")
+        got = (minimum_sets_nr if r["prioritise_nr"] else minimum_sets)(h, valid, 2, review=review)
+        key = (r["fasta"], r["pam"], r["prioritise_nr"])
+        if r["stable_across_hash_seeds"]:
+            assert shown == r["shown"], key
+            assert [sorted(s) for s in got] == r["sets"], key
+        else:
+            assert [len(s) for s in got] == [len(s) for s in r["sets"]] and len(shown) == 5, key
+        rejected = {r["shown"][0][1][0][1], dict((i, s) for i, s in r["shown"][1][1])[r["shown"][1][1][0][0]]}
+        if r["stable_across_hash_seeds"]:
+            assert not rejected & {s for g in got for s in g}, key
