@@ -504,7 +504,7 @@ class MINORg:
         to 5' -> least redundant -> first; or, with self.prioritise_nr, the non-redundancy-first covers of
         minimum_set_nr.py).  manual=True shows every drawn set on the terminal and lets the user reject gRNA by id or
         sequence before it is accepted (minimum_set.py:43-64, 603-637; the reference's default unless --auto, here opt-in).
-        `fasta` renaming and the .eqv file are not provided (outside the hot path)."""
+        Also writes <prefix>_gRNA_pass.eqv (coverage groups of the passing gRNA).  `fasta` renaming is not provided."""
         if not self.grna_hits:
             raise MINORgError("MINORg.minimumset requires gRNA. You may read a mapping file using"
                               " self.grna_hits.parse_from_mapping('<path to file>') or use self.grna() to generate gRNA.")
@@ -525,6 +525,10 @@ class MINORg:
             print("Final gRNA sequence ID(s), gRNA sequence(s), and target(s) have been written to %s"
                   % (fout_map if report_full_path else os.path.basename(fout_map)))
             self.final_map = fout_map
+            fout_eqv = fout_eqv or self.results_fname("gRNA_pass.eqv")           # MINORg.py:2645-2647
+            self.grna_hits.write_equivalents(fout_eqv, seqs=valid)
+            print("Groupings of passing gRNA with equivalent coverage have been written to %s"
+                  % (fout_eqv if report_full_path else os.path.basename(fout_eqv)))
         print("\n%d mutually exclusive gRNA set(s) requested. %d set(s) found." % (sets, len(grna_sets)))
         return grna_sets
 
